@@ -1,0 +1,130 @@
+"""ctypes binding of the C-ABI library (include/b200rnn.h).
+
+There is no CPU fallback by design: if ``lib/libb200rnn.so`` is missing or does not export the symbols the
+header declares, importing the compute entry points fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200rnn.so")
+
+GRU, LSTM = 0, 1
+FLAG_ACCUMULATE_GRADS = 1
+FLAG_SAVE_FOR_BACKWARD = 2
+ABI_VERSION = 1
+
+# every symbol include/b200rnn.h declares (tests check the .so exports exactly these)
+SYMBOLS = (
+    "b200rnn_version",
+    "b200rnn_last_error",
+    "b200rnn_sm_count",
+    "b200rnn_workspace_bytes",
+    "b200rnn_forward",
+    "b200rnn_backward",
+    "b200rnn_gemm_f32",
+)
+
+
+class Desc(ctypes.Structure):
+    """``b200rnn_desc`` (include/b200rnn.h)."""
+
+    _fields_ = [
+        ("mode", c_int32),
+        ("batch", c_int32),
+        ("seq_len", c_int32),
+        ("input_size", c_int32),
+        ("hidden_size", c_int32),
+        ("num_layers", c_int32),
+        ("num_dirs", c_int32),
+        ("training", c_int32),
+        ("dropout_p", c_float),
+        ("flags", c_uint32),
+    ]
+
+
+class B200RNNError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and type the shared library. Raises if it is absent — no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200RNNError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C icassp2022-depression_b200`). b200rnn has no CPU / PyTorch fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    missing = [s for s in SYMBOLS if not hasattr(lib, s)]
+    if missing:
+        raise B200RNNError(f"{LIB_PATH} does not export {missing}")
+    fp = POINTER(c_float)
+    lib.b200rnn_version.restype = c_int
+    lib.b200rnn_version.argtypes = []
+    lib.b200rnn_last_error.restype = c_char_p
+    lib.b200rnn_last_error.argtypes = []
+    lib.b200rnn_sm_count.restype = c_int
+    lib.b200rnn_sm_count.argtypes = []
+    lib.b200rnn_workspace_bytes.restype = c_int
+    lib.b200rnn_workspace_bytes.argtypes = [POINTER(Desc), POINTER(c_size_t), POINTER(c_size_t)]
+    lib.b200rnn_forward.restype = c_int
+    lib.b200rnn_forward.argtypes = [
+        POINTER(Desc), c_void_p, c_int64, c_int64,  # desc, x, strides
+        POINTER(c_void_p),                           # params
+        c_void_p, c_int64, c_int64,                  # y, strides
+        c_void_p, c_void_p,                          # h_n, c_n
+        c_void_p, c_void_p,                          # reserve, scratch
+        c_uint64, c_uint64, c_void_p,                # seed, offset, rng_state
+        c_void_p,                                    # stream
+    ]
+    lib.b200rnn_backward.restype = c_int
+    lib.b200rnn_backward.argtypes = [
+        POINTER(Desc), c_void_p, c_int64, c_int64,   # desc, x, strides
+        POINTER(c_void_p),                           # params
+        c_void_p, c_int64, c_int64,                  # y
+        c_void_p, c_int64, c_int64,                  # dy
+        c_void_p, c_void_p,                          # dh_n, dc_n
+        c_void_p, c_void_p,                          # reserve, scratch
+        c_void_p, c_int64, c_int64,                  # dx
+        POINTER(c_void_p),                           # dparams
+        c_void_p,                                    # stream
+    ]
+    lib.b200rnn_gemm_f32.restype = c_int
+    lib.b200rnn_gemm_f32.argtypes = [
+        c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p,
+        c_int, c_void_p, c_size_t, c_void_p,
+    ]
+    del fp
+    v = lib.b200rnn_version()
+    if v != ABI_VERSION:
+        raise B200RNNError(f"ABI mismatch: library {v}, binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().b200rnn_last_error().decode("utf-8", "replace")
+        raise B200RNNError(f"{what} failed (code {rc}): {msg}")
+
+
+def workspace_bytes(desc: Desc) -> tuple[int, int]:
+    r, s = c_size_t(0), c_size_t(0)
+    check(load().b200rnn_workspace_bytes(ctypes.byref(desc), ctypes.byref(r), ctypes.byref(s)), "workspace_bytes")
+    return int(r.value), int(s.value)
+
+
+def ptr_array(ptrs) -> ctypes.Array:
+    arr = (c_void_p * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr

@@ -1,0 +1,224 @@
+"""Autograd bridge between PyTorch tensors and the C-ABI library.
+
+``rnn_forward`` is what ``b200rnn.GRU.forward`` / ``b200rnn.LSTM.forward`` call in place of ``_VF.gru`` /
+``_VF.lstm`` (torch/nn/modules/rnn.py:1449 / :1169). PyTorch is only plumbing here: it owns the device
+memory (``torch.empty`` -> caching allocator, CUDA-graph friendly) and the current stream; all arithmetic
+happens in ``lib/libb200rnn.so``. CPU tensors are rejected — there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class RNNConfig:
+    mode: int            # _lib.GRU / _lib.LSTM
+    input_size: int
+    hidden_size: int
+    num_layers: int
+    num_dirs: int
+    dropout: float
+    training: bool
+    batch_first: bool
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.B200RNNError(
+            f"b200rnn: {name} is on {t.device}; this library runs on CUDA (sm_100a) only and has no CPU path"
+        )
+    if t.dtype != torch.float32:
+        raise _lib.B200RNNError(f"b200rnn: {name} must be float32 (got {t.dtype})")
+
+
+def _tm_view(x: torch.Tensor) -> torch.Tensor:
+    """Return a logical [T,B,F] tensor whose feature stride is 1 (copy only if it is not)."""
+    if x.stride(2) != 1 and x.size(2) != 1:
+        x = x.contiguous()
+    return x
+
+
+def _make_desc(cfg: RNNConfig, B: int, T: int, save: bool, accumulate: bool = False) -> _lib.Desc:
+    flags = 0
+    if save:
+        flags |= _lib.FLAG_SAVE_FOR_BACKWARD
+    if accumulate:
+        flags |= _lib.FLAG_ACCUMULATE_GRADS
+    return _lib.Desc(cfg.mode, B, T, cfg.input_size, cfg.hidden_size, cfg.num_layers, cfg.num_dirs,
+                     1 if cfg.training else 0, float(cfg.dropout), flags)
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _RNNFunction(torch.autograd.Function):
+    """y, h_n[, c_n] = RNN(x, weights); x is the logical time-major view [T,B,I]."""
+
+    @staticmethod
+    def forward(ctx, x_tm: torch.Tensor, cfg: RNNConfig, rng_state: Optional[torch.Tensor], grad_sink,
+                *weights: torch.Tensor):
+        lib = _lib.load()
+        T, B, _ = x_tm.shape
+        H, L, D = cfg.hidden_size, cfg.num_layers, cfg.num_dirs
+        dev = x_tm.device
+        save = any(ctx.needs_input_grad)
+        desc = _make_desc(cfg, B, T, save)
+        rbytes, sbytes = _lib.workspace_bytes(desc)
+        reserve = torch.empty(rbytes if save else 0, dtype=torch.uint8, device=dev)
+        scratch = torch.empty(0 if save else sbytes, dtype=torch.uint8, device=dev)
+        if cfg.batch_first:
+            y = torch.empty(B, T, D * H, dtype=torch.float32, device=dev)
+            ys_t, ys_b = D * H, T * D * H
+        else:
+            y = torch.empty(T, B, D * H, dtype=torch.float32, device=dev)
+            ys_t, ys_b = B * D * H, D * H
+        h_n = torch.empty(L * D, B, H, dtype=torch.float32, device=dev)
+        c_n = torch.empty(L * D, B, H, dtype=torch.float32, device=dev) if cfg.mode == _lib.LSTM else None
+        params = _lib.ptr_array([w.data_ptr() for w in weights])
+        if B > 0 and T > 0:
+            rc = lib.b200rnn_forward(
+                ctypes.byref(desc), x_tm.data_ptr(), x_tm.stride(0), x_tm.stride(1), params,
+                y.data_ptr(), ys_t, ys_b, h_n.data_ptr(), c_n.data_ptr() if c_n is not None else None,
+                reserve.data_ptr() if save else None, scratch.data_ptr() if not save else None,
+                0, 0, rng_state.data_ptr() if rng_state is not None else None, _stream_ptr())
+            _lib.check(rc, "b200rnn_forward")
+        else:
+            h_n.zero_()
+            if c_n is not None:
+                c_n.zero_()
+        if save:
+            ctx.cfg = cfg
+            ctx.grad_sink = grad_sink
+            ctx.ys = (ys_t, ys_b)
+            ctx.save_for_backward(x_tm, y, reserve, *weights)
+        if c_n is None:
+            return y, h_n
+        return y, h_n, c_n
+
+    @staticmethod
+    def backward(ctx, dy, dh_n, dc_n=None):
+        lib = _lib.load()
+        cfg: RNNConfig = ctx.cfg
+        x_tm, y, reserve, *weights = ctx.saved_tensors
+        T, B, _ = x_tm.shape
+        H, L, D = cfg.hidden_size, cfg.num_layers, cfg.num_dirs
+        dev = x_tm.device
+        ys_t, ys_b = ctx.ys
+
+        if dy is None:
+            dy = torch.zeros_like(y)
+        if dy.stride(2) != 1 and dy.size(2) != 1:
+            dy = dy.contiguous()
+        if cfg.batch_first:
+            dys_t, dys_b = dy.stride(1), dy.stride(0)
+        else:
+            dys_t, dys_b = dy.stride(0), dy.stride(1)
+        if dh_n is not None:
+            dh_n = dh_n.contiguous()
+        if dc_n is not None:
+            dc_n = dc_n.contiguous()
+
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty_like(x_tm) if need_dx else None
+        if dx is not None and dx.stride(2) != 1 and dx.size(2) != 1:
+            dx = torch.empty(x_tm.shape, dtype=torch.float32, device=dev)
+
+        # weight gradients: either straight into caller-provided views (a flat all-reduce bucket) or into one
+        # fresh flat buffer that is returned to autograd as views
+        sink = ctx.grad_sink
+        w_needed = [ctx.needs_input_grad[4 + i] for i in range(len(weights))]
+        grads_out: list = [None] * len(weights)
+        accumulate = False
+        if sink is not None:
+            targets = sink(weights)  # list of tensors (same shapes) or None entries
+            accumulate = True
+            dptrs = [t.data_ptr() if (t is not None and n) else None for t, n in zip(targets, w_needed)]
+        else:
+            sizes = [w.numel() if n else 0 for w, n in zip(weights, w_needed)]
+            flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            dptrs, off = [], 0
+            for i, (w, n) in enumerate(zip(weights, w_needed)):
+                if n:
+                    g = flat[off:off + w.numel()].view_as(w)
+                    off += w.numel()
+                    grads_out[i] = g
+                    dptrs.append(g.data_ptr())
+                else:
+                    dptrs.append(None)
+
+        desc = _make_desc(cfg, B, T, True, accumulate)
+        _, sbytes = _lib.workspace_bytes(desc)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+        params = _lib.ptr_array([w.data_ptr() for w in weights])
+        dparams = _lib.ptr_array(dptrs)
+        if B > 0 and T > 0:
+            rc = lib.b200rnn_backward(
+                ctypes.byref(desc), x_tm.data_ptr(), x_tm.stride(0), x_tm.stride(1), params,
+                y.data_ptr(), ys_t, ys_b, dy.data_ptr(), dys_t, dys_b,
+                dh_n.data_ptr() if dh_n is not None else None,
+                dc_n.data_ptr() if dc_n is not None else None,
+                reserve.data_ptr(), scratch.data_ptr(),
+                dx.data_ptr() if dx is not None else None,
+                dx.stride(0) if dx is not None else 0, dx.stride(1) if dx is not None else 0,
+                dparams, _stream_ptr())
+            _lib.check(rc, "b200rnn_backward")
+        else:
+            for g in grads_out:
+                if g is not None:
+                    g.zero_()
+        return (dx, None, None, None, *grads_out)
+
+
+def rnn_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNNConfig,
+                rng_state: Optional[torch.Tensor] = None, grad_sink=None):
+    """Run the multi-layer GRU/LSTM. ``x`` is [T,B,I] (or [B,T,I] if ``cfg.batch_first``), any strides.
+
+    Returns ``(y, h_n)`` for GRU and ``(y, h_n, c_n)`` for LSTM, laid out like torch.nn.GRU/LSTM outputs.
+    """
+    _require_cuda_f32(x, "input")
+    if x.dim() != 3:
+        raise NotImplementedError("b200rnn: only batched 3-D input is supported (the reference never uses 2-D)")
+    for i, w in enumerate(weights):
+        _require_cuda_f32(w, f"weight[{i}]")
+        if not w.is_contiguous():
+            raise _lib.B200RNNError(f"b200rnn: weight[{i}] must be contiguous")
+    if x.size(2) != cfg.input_size:
+        raise RuntimeError(f"input.size(-1) must be equal to input_size. Expected {cfg.input_size}, got {x.size(2)}")
+    x_tm = x.transpose(0, 1) if cfg.batch_first else x
+    x_tm = _tm_view(x_tm)
+    return _RNNFunction.apply(x_tm, cfg, rng_state, grad_sink, *weights)
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kcontig: bool = True, b_kcontig: bool = True,
+         bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, accumulate: bool = False,
+         use_splitk: bool = True) -> torch.Tensor:
+    """C = A(m,k) B(k,n) (+bias) through ``b200rnn_gemm_f32`` — exposed for the parity tests.
+
+    a: [M,K] if a_kcontig else [K,M];  b: [N,K] if b_kcontig else [K,N]; row-major, last stride 1.
+    """
+    lib = _lib.load()
+    _require_cuda_f32(a, "a")
+    _require_cuda_f32(b, "b")
+    M, K = (a.shape if a_kcontig else (a.shape[1], a.shape[0]))
+    N = b.shape[0] if b_kcontig else b.shape[1]
+    Kb = b.shape[1] if b_kcontig else b.shape[0]
+    assert K == Kb, (a.shape, b.shape)
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+        assert not accumulate
+    sbytes = M * N * 4 * 64 if use_splitk else 0
+    scratch = torch.empty(sbytes, dtype=torch.uint8, device=a.device) if sbytes else None
+    rc = lib.b200rnn_gemm_f32(M, N, K, a.data_ptr(), a.stride(0), int(a_kcontig), b.data_ptr(), b.stride(0),
+                              int(b_kcontig), out.data_ptr(), out.stride(0),
+                              bias.data_ptr() if bias is not None else None, int(accumulate),
+                              scratch.data_ptr() if scratch is not None else None, sbytes, _stream_ptr())
+    _lib.check(rc, "b200rnn_gemm_f32")
+    return out

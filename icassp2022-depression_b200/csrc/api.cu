@@ -1,0 +1,472 @@
+// api.cu — the C ABI (include/b200rnn.h) and the host-side sequencing of one multi-layer GRU / (Bi)LSTM
+// forward or backward pass. Everything is enqueued on the caller's stream; no allocation, no sync.
+//
+// Per layer, forward:   [K1 GEMM per direction]  ->  [one persistent recurrence launch, all directions]
+//                       -> [K7 dropout, train mode, not after the last layer]
+// Per layer, backward:  [W_hh transpose per direction] -> [one persistent BPTT launch, all directions]
+//                       -> [bias reduce, wgrad GEMMs (split-K, deterministic), dgrad GEMM]
+#include <mutex>
+#include <stdarg.h>
+#include <string.h>
+
+#include "gemm_f32.cuh"
+#include "misc_kernels.cuh"
+#include "rnn_kernels.cuh"
+
+namespace b200rnn {
+
+static thread_local char g_err[512] = {0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Dims {
+  int mode, B, T, I, H, L, D, G;
+  size_t TB, GH, DH;
+  bool training;
+  float p;
+};
+
+int check_desc(const b200rnn_desc* d, Dims* o) {
+  if (!d) {
+    set_error("null descriptor");
+    return B200RNN_ERR_INVALID;
+  }
+  if (d->mode != B200RNN_GRU && d->mode != B200RNN_LSTM) {
+    set_error("mode must be B200RNN_GRU or B200RNN_LSTM (got %d)", d->mode);
+    return B200RNN_ERR_INVALID;
+  }
+  if (d->batch < 0 || d->seq_len < 0 || d->input_size <= 0 || d->num_layers <= 0 ||
+      (d->num_dirs != 1 && d->num_dirs != 2)) {
+    set_error("bad shape: B=%d T=%d I=%d L=%d D=%d", d->batch, d->seq_len, d->input_size, d->num_layers,
+              d->num_dirs);
+    return B200RNN_ERR_INVALID;
+  }
+  if (d->hidden_size != 128 && d->hidden_size != 256) {
+    set_error("hidden_size %d unsupported: the sm_100a persistent kernels are built for 128 and 256",
+              d->hidden_size);
+    return B200RNN_ERR_UNSUPPORTED;
+  }
+  if (!(d->dropout_p >= 0.f && d->dropout_p <= 1.f)) {
+    set_error("dropout_p must be in [0,1] (got %f)", (double)d->dropout_p);
+    return B200RNN_ERR_INVALID;
+  }
+  o->mode = d->mode;
+  o->B = d->batch;
+  o->T = d->seq_len;
+  o->I = d->input_size;
+  o->H = d->hidden_size;
+  o->L = d->num_layers;
+  o->D = d->num_dirs;
+  o->G = d->mode == B200RNN_GRU ? 3 : 4;
+  o->TB = (size_t)d->seq_len * d->batch;
+  o->GH = (size_t)o->G * o->H;
+  o->DH = (size_t)o->D * o->H;
+  o->training = d->training != 0;
+  o->p = d->dropout_p;
+  return B200RNN_OK;
+}
+
+constexpr size_t ALIGN_F = 64;  // floats (256 B)
+
+// ---- reserve layout (floats) ------------------------------------------------------------------
+struct ReserveLayout {
+  size_t gates[8][2], extra[8][2];  // up to 8 layers
+  size_t ylayer[8], ydrop[8];
+  size_t total;
+};
+
+int make_reserve(const Dims& d, ReserveLayout* r) {
+  if (d.L > 8) {
+    set_error("num_layers %d > 8 unsupported", d.L);
+    return B200RNN_ERR_UNSUPPORTED;
+  }
+  size_t off = ALIGN_F;  // [0, ALIGN_F): header {dropout seed, dropout offset} written by the forward
+  for (int l = 0; l < d.L; ++l)
+    for (int k = 0; k < d.D; ++k) {
+      r->gates[l][k] = off;
+      off += align_up(d.TB * d.GH, ALIGN_F);
+      r->extra[l][k] = off;
+      off += align_up(d.TB * d.H, ALIGN_F);
+    }
+  for (int l = 0; l + 1 < d.L; ++l) {
+    r->ylayer[l] = off;
+    off += align_up(d.TB * d.DH, ALIGN_F);
+    r->ydrop[l] = off;
+    if (d.p > 0.f) off += align_up(d.TB * d.DH, ALIGN_F);
+  }
+  r->total = off;
+  return B200RNN_OK;
+}
+
+// ---- scratch layout (floats) ------------------------------------------------------------------
+struct ScratchLayout {
+  // forward, inference
+  size_t f_gates[2], f_y[2];
+  size_t f_total;
+  // backward
+  size_t b_dgates[2], b_dghn[2], b_wt[2], b_bpart[2], b_dy, b_gemm;
+  size_t b_gemm_bytes;
+  size_t b_total;
+};
+
+void make_scratch(const Dims& d, ScratchLayout* s) {
+  size_t off = ALIGN_F;  // header (dropout seed/offset when nothing is saved for backward)
+  for (int k = 0; k < d.D; ++k) {
+    s->f_gates[k] = off;
+    off += align_up(d.TB * d.GH, ALIGN_F);
+  }
+  for (int k = 0; k < 2; ++k) {
+    s->f_y[k] = off;
+    off += align_up(d.TB * d.DH, ALIGN_F);
+  }
+  s->f_total = off;
+
+  off = 0;
+  for (int k = 0; k < d.D; ++k) {
+    s->b_dgates[k] = off;
+    off += align_up(d.TB * d.GH, ALIGN_F);
+    s->b_dghn[k] = off;
+    off += align_up(d.TB * d.H, ALIGN_F);
+    s->b_wt[k] = off;
+    off += align_up(d.GH * d.H, ALIGN_F);
+    s->b_bpart[k] = off;
+    off += align_up((size_t)rec_bwd_max_slices(d.B) * (d.G + 1) * d.H, ALIGN_F);
+  }
+  s->b_dy = off;
+  off += align_up(d.TB * d.DH, ALIGN_F);
+  size_t gb = 0;
+  const int K = (int)d.TB;
+  size_t g0 = gemm_scratch_bytes((int)d.GH, d.I, K);
+  size_t g1 = gemm_scratch_bytes((int)d.GH, (int)d.DH, K);
+  size_t g2 = gemm_scratch_bytes((int)d.GH, d.H, K);
+  gb = g0 > g1 ? g0 : g1;
+  gb = gb > g2 ? gb : g2;
+  s->b_gemm = off;
+  s->b_gemm_bytes = gb;
+  off += align_up(gb / sizeof(float) + 1, ALIGN_F);
+  s->b_total = off;
+}
+
+inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+}  // namespace
+}  // namespace b200rnn
+
+using namespace b200rnn;
+
+extern "C" {
+
+B200RNN_API int b200rnn_version(void) { return B200RNN_ABI_VERSION; }
+
+B200RNN_API const char* b200rnn_last_error(void) { return g_err; }
+
+B200RNN_API int b200rnn_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    set_error("cannot query the CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    return B200RNN_ERR_CUDA;
+  }
+  return n;
+}
+
+B200RNN_API int b200rnn_workspace_bytes(const b200rnn_desc* desc, size_t* reserve_bytes, size_t* scratch_bytes) {
+  Dims d;
+  int rc = check_desc(desc, &d);
+  if (rc) return rc;
+  ReserveLayout r;
+  rc = make_reserve(d, &r);
+  if (rc) return rc;
+  ScratchLayout s;
+  make_scratch(d, &s);
+  if (reserve_bytes) *reserve_bytes = (r.total + ALIGN_F) * sizeof(float);
+  if (scratch_bytes) *scratch_bytes = ((s.f_total > s.b_total ? s.f_total : s.b_total) + ALIGN_F) * sizeof(float);
+  return B200RNN_OK;
+}
+
+B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_t xs_t, int64_t xs_b,
+                                const float* const* params, float* y, int64_t ys_t, int64_t ys_b, float* h_n,
+                                float* c_n, void* reserve, void* scratch, uint64_t seed, uint64_t offset,
+                                uint64_t* rng_state, void* stream_) {
+  Dims d;
+  int rc = check_desc(desc, &d);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (d.B == 0 || d.T == 0) return B200RNN_OK;
+  const bool save = (desc->flags & B200RNN_FLAG_SAVE_FOR_BACKWARD) != 0;
+  if (!x || !params || !y || !h_n || (d.mode == B200RNN_LSTM && !c_n)) {
+    set_error("forward: null pointer argument");
+    return B200RNN_ERR_INVALID;
+  }
+  if (save && !reserve) {
+    set_error("forward: B200RNN_FLAG_SAVE_FOR_BACKWARD needs a reserve buffer");
+    return B200RNN_ERR_INVALID;
+  }
+  if (!save && !scratch) {
+    set_error("forward: a scratch buffer is required when nothing is saved for backward");
+    return B200RNN_ERR_INVALID;
+  }
+  if ((reserve && !aligned_to(reserve, 256)) || (scratch && !aligned_to(scratch, 256))) {
+    set_error("forward: reserve/scratch must be 256-byte aligned");
+    return B200RNN_ERR_INVALID;
+  }
+  ReserveLayout rl;
+  rc = make_reserve(d, &rl);
+  if (rc) return rc;
+  ScratchLayout sl;
+  make_scratch(d, &sl);
+  float* R = static_cast<float*>(reserve);
+  float* S = static_cast<float*>(scratch);
+  const bool drop = d.training && d.p > 0.f && d.L > 1;
+  uint64_t* hdr = reinterpret_cast<uint64_t*>(save ? R : S);
+  if (drop || save) {
+    rc = launch_rng_setup(hdr, seed, offset, rng_state, drop ? (uint64_t)((d.TB * d.DH + 3) / 4) : 0, st);
+    if (rc) return rc;
+  }
+
+  for (int l = 0; l < d.L; ++l) {
+    const int Il = l == 0 ? d.I : (int)d.DH;
+    // ---- layer input ---------------------------------------------------------------------------
+    const float* in;
+    RowMap in_rows;
+    if (l == 0) {
+      in = x;
+      in_rows = tb_rows(xs_t, xs_b, d.B);
+    } else {
+      if (save)
+        in = R + (drop ? rl.ydrop[l - 1] : rl.ylayer[l - 1]);
+      else
+        in = S + sl.f_y[(l - 1) & 1];
+      in_rows = simple_rows((long long)d.DH);
+    }
+    RecFwdParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.mode = d.mode; rp.B = d.B; rp.T = d.T; rp.H = d.H; rp.D = d.D;
+    rp.training = save ? 1 : 0;
+    for (int k = 0; k < d.D; ++k) {
+      const float* const* pp = params + (size_t)(l * d.D + k) * 4;
+      const float *w_ih = pp[0], *w_hh = pp[1], *b_ih = pp[2], *b_hh = pp[3];
+      if (!w_ih || !w_hh || !b_ih || !b_hh) {
+        set_error("forward: null parameter pointer (layer %d dir %d)", l, k);
+        return B200RNN_ERR_INVALID;
+      }
+      if (!aligned_to(w_hh, 16)) {
+        set_error("forward: weight_hh must be 16-byte aligned for the TMA bulk copy (layer %d dir %d)", l, k);
+        return B200RNN_ERR_INVALID;
+      }
+      float* gates = save ? R + rl.gates[l][k] : S + sl.f_gates[k];
+      // K1: x-projection of every time step at once, biases folded (GRU: b_hh only for r,z)
+      GemmParams g;
+      memset(&g, 0, sizeof(g));
+      g.A = in; g.a_rows = in_rows; g.a_kcontig = 1;
+      g.B = w_ih; g.b_rows = simple_rows(Il); g.b_kcontig = 1;
+      g.C = gates; g.c_rows = simple_rows((long long)d.GH);
+      g.M = (int)d.TB; g.N = (int)d.GH; g.K = Il;
+      g.bias1 = b_ih; g.bias2 = b_hh;
+      g.bias2_n = d.mode == B200RNN_GRU ? 2 * d.H : 4 * d.H;
+      rc = launch_gemm(g, nullptr, 0, st);
+      if (rc) return rc;
+      rp.w_hh[k] = w_hh;
+      rp.b_hh[k] = b_hh;
+      rp.gates[k] = gates;
+      rp.extra[k] = save ? R + rl.extra[l][k] : nullptr;
+    }
+    float* ylay = nullptr;
+    if (l == d.L - 1) {
+      rp.y = y; rp.y_st = ys_t; rp.y_sb = ys_b;
+    } else {
+      ylay = save ? R + rl.ylayer[l] : S + sl.f_y[l & 1];
+      rp.y = ylay;
+      rp.y_st = (long long)d.B * d.DH; rp.y_sb = (long long)d.DH;
+    }
+    rp.h_n = h_n + (size_t)l * d.D * d.B * d.H;
+    rp.c_n = c_n ? c_n + (size_t)l * d.D * d.B * d.H : nullptr;
+    rc = launch_rec_fwd(rp, st);
+    if (rc) return rc;
+    if (drop && l + 1 < d.L) {  // K7; keeps the raw output when it is needed by backward, else in place
+      rc = launch_dropout(ylay, save ? R + rl.ydrop[l] : ylay, d.TB * d.DH, d.p, hdr, (uint32_t)l, st);
+      if (rc) return rc;
+    }
+  }
+  return B200RNN_OK;
+}
+
+B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64_t xs_t, int64_t xs_b,
+                                 const float* const* params, const float* y, int64_t ys_t, int64_t ys_b,
+                                 const float* dy, int64_t dys_t, int64_t dys_b, const float* dh_n,
+                                 const float* dc_n, const void* reserve, void* scratch, float* dx, int64_t dxs_t,
+                                 int64_t dxs_b, float* const* dparams, void* stream_) {
+  Dims d;
+  int rc = check_desc(desc, &d);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (d.B == 0 || d.T == 0) return B200RNN_OK;
+  if (!x || !params || !y || !dy || !reserve || !scratch || !dparams) {
+    set_error("backward: null pointer argument");
+    return B200RNN_ERR_INVALID;
+  }
+  if (!aligned_to(reserve, 256) || !aligned_to(scratch, 256)) {
+    set_error("backward: reserve/scratch must be 256-byte aligned");
+    return B200RNN_ERR_INVALID;
+  }
+  ReserveLayout rl;
+  rc = make_reserve(d, &rl);
+  if (rc) return rc;
+  ScratchLayout sl;
+  make_scratch(d, &sl);
+  const float* R = static_cast<const float*>(reserve);
+  float* S = static_cast<float*>(scratch);
+  const bool drop = d.training && d.p > 0.f && d.L > 1;
+  const uint64_t* hdr = reinterpret_cast<const uint64_t*>(R);  // dropout seed/offset used by the forward
+  const int accumulate = (desc->flags & B200RNN_FLAG_ACCUMULATE_GRADS) ? 1 : 0;
+  void* gemm_ws = sl.b_gemm_bytes ? (void*)(S + sl.b_gemm) : nullptr;
+
+  for (int l = d.L - 1; l >= 0; --l) {
+    const int Il = l == 0 ? d.I : (int)d.DH;
+    RecBwdParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.mode = d.mode; bp.B = d.B; bp.T = d.T; bp.H = d.H; bp.D = d.D;
+    if (l == d.L - 1) {
+      bp.y = y; bp.y_st = ys_t; bp.y_sb = ys_b;
+      bp.dy = dy; bp.dy_st = dys_t; bp.dy_sb = dys_b;
+    } else {
+      bp.y = R + rl.ylayer[l]; bp.y_st = (long long)d.B * d.DH; bp.y_sb = (long long)d.DH;
+      bp.dy = S + sl.b_dy; bp.dy_st = (long long)d.B * d.DH; bp.dy_sb = (long long)d.DH;
+    }
+    bp.dh_n = dh_n ? dh_n + (size_t)l * d.D * d.B * d.H : nullptr;
+    bp.dc_n = dc_n ? dc_n + (size_t)l * d.D * d.B * d.H : nullptr;
+    for (int k = 0; k < d.D; ++k) {
+      const float* const* pp = params + (size_t)(l * d.D + k) * 4;
+      if (!pp[0] || !pp[1]) {
+        set_error("backward: null parameter pointer (layer %d dir %d)", l, k);
+        return B200RNN_ERR_INVALID;
+      }
+      rc = launch_transpose(pp[1], S + sl.b_wt[k], (int)d.GH, d.H, st);  // W_hh [GH,H] -> [H,GH]
+      if (rc) return rc;
+      bp.w_hh_t[k] = S + sl.b_wt[k];
+      bp.gates[k] = R + rl.gates[l][k];
+      bp.extra[k] = R + rl.extra[l][k];
+      bp.dgates[k] = S + sl.b_dgates[k];
+      bp.dghn[k] = S + sl.b_dghn[k];
+      bp.dbias_part[k] = S + sl.b_bpart[k];
+    }
+    rc = launch_rec_bwd(bp, st);
+    if (rc) return rc;
+
+    // layer input as seen by the forward GEMM
+    const float* in;
+    RowMap in_rows;
+    if (l == 0) {
+      in = x;
+      in_rows = tb_rows(xs_t, xs_b, d.B);
+    } else {
+      in = R + (drop ? rl.ydrop[l - 1] : rl.ylayer[l - 1]);
+      in_rows = simple_rows((long long)d.DH);
+    }
+    const bool want_dx = (l > 0) || (dx != nullptr);
+    for (int k = 0; k < d.D; ++k) {
+      const float* const* pp = params + (size_t)(l * d.D + k) * 4;
+      float* const* gp = dparams + (size_t)(l * d.D + k) * 4;
+      float *dw_ih = gp[0], *dw_hh = gp[1], *db_ih = gp[2], *db_hh = gp[3];
+      const float* dG = S + sl.b_dgates[k];
+      const float* dHN = S + sl.b_dghn[k];
+      if (db_ih || db_hh) {
+        rc = launch_bias_reduce(S + sl.b_bpart[k], bp.nslices_out, d.mode, d.H, db_ih, db_hh, accumulate, st);
+        if (rc) return rc;
+      }
+      if (dw_ih) {  // dW_ih = dGi^T * X_l
+        GemmParams g;
+        memset(&g, 0, sizeof(g));
+        g.A = dG; g.a_rows = simple_rows((long long)d.GH); g.a_kcontig = 0;
+        g.B = in; g.b_rows = in_rows; g.b_kcontig = 0;
+        g.C = dw_ih; g.c_rows = simple_rows(Il);
+        g.M = (int)d.GH; g.N = Il; g.K = (int)d.TB;
+        g.accumulate = accumulate;
+        rc = launch_gemm(g, gemm_ws, sl.b_gemm_bytes, st);
+        if (rc) return rc;
+      }
+      if (dw_hh) {  // dW_hh = sum_t dGh[t]^T * h_{prev(t)}   (h_prev of the first scanned step is 0)
+        const int Kp = (d.T - 1) * d.B;
+        // forward direction: pairs (dG[t], y[t-1]) for t = 1..T-1 ; reverse: (dG[t], y[t+1]) for t = 0..T-2
+        const size_t g_t0 = (k == 0) ? (size_t)d.B : 0;  // first dG row
+        const long long y_t0 = (k == 0) ? 0 : bp.y_st;   // first y row offset (elements)
+        const float* hp = bp.y + y_t0 + (long long)k * d.H;
+        RowMap hp_rows = tb_rows(bp.y_st, bp.y_sb, d.B);
+        GemmParams g;
+        memset(&g, 0, sizeof(g));
+        g.B = hp; g.b_rows = hp_rows; g.b_kcontig = 0;
+        g.N = d.H; g.K = Kp;
+        g.accumulate = accumulate;
+        g.a_kcontig = 0;
+        if (d.mode == B200RNN_LSTM) {
+          g.A = dG + g_t0 * d.GH; g.a_rows = simple_rows((long long)d.GH);
+          g.C = dw_hh; g.c_rows = simple_rows(d.H);
+          g.M = (int)d.GH;
+          rc = launch_gemm(g, gemm_ws, sl.b_gemm_bytes, st);
+          if (rc) return rc;
+        } else {
+          // r,z rows share dGi; the n rows use dn*r
+          g.A = dG + g_t0 * d.GH; g.a_rows = simple_rows((long long)d.GH);
+          g.C = dw_hh; g.c_rows = simple_rows(d.H);
+          g.M = 2 * d.H;
+          rc = launch_gemm(g, gemm_ws, sl.b_gemm_bytes, st);
+          if (rc) return rc;
+          g.A = dHN + g_t0 * d.H; g.a_rows = simple_rows((long long)d.H);
+          g.C = dw_hh + (size_t)2 * d.H * d.H;
+          g.M = d.H;
+          rc = launch_gemm(g, gemm_ws, sl.b_gemm_bytes, st);
+          if (rc) return rc;
+        }
+      }
+      if (want_dx) {  // dX_l (+)= dGi * W_ih
+        GemmParams g;
+        memset(&g, 0, sizeof(g));
+        g.A = dG; g.a_rows = simple_rows((long long)d.GH); g.a_kcontig = 1;
+        g.B = pp[0]; g.b_rows = simple_rows(Il); g.b_kcontig = 0;
+        if (l == 0) {
+          g.C = dx; g.c_rows = tb_rows(dxs_t, dxs_b, d.B);
+        } else {
+          g.C = S + sl.b_dy; g.c_rows = simple_rows((long long)d.DH);
+        }
+        g.M = (int)d.TB; g.N = Il; g.K = (int)d.GH;
+        g.accumulate = (k > 0) ? 1 : 0;
+        rc = launch_gemm(g, nullptr, 0, st);
+        if (rc) return rc;
+      }
+    }
+    if (l > 0 && drop) {  // gradient through the inter-layer dropout of layer l-1's output (same mask)
+      rc = launch_dropout(S + sl.b_dy, S + sl.b_dy, d.TB * d.DH, d.p, hdr, (uint32_t)(l - 1), st);
+      if (rc) return rc;
+    }
+  }
+  return B200RNN_OK;
+}
+
+B200RNN_API int b200rnn_gemm_f32(int M, int N, int K, const float* A, int64_t lda, int a_kcontig, const float* B,
+                     int64_t ldb, int b_kcontig, float* C, int64_t ldc, const float* bias, int accumulate,
+                     void* scratch, size_t scratch_bytes, void* stream_) {
+  if (M < 0 || N < 0 || K < 0) {
+    set_error("gemm: negative dimension");
+    return B200RNN_ERR_INVALID;
+  }
+  GemmParams g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.a_rows = simple_rows(lda); g.a_kcontig = a_kcontig;
+  g.B = B; g.b_rows = simple_rows(ldb); g.b_kcontig = b_kcontig;
+  g.C = C; g.c_rows = simple_rows(ldc);
+  g.M = M; g.N = N; g.K = K;
+  g.bias1 = bias;
+  g.accumulate = accumulate;
+  return launch_gemm(g, scratch, scratch_bytes, static_cast<cudaStream_t>(stream_));
+}
+
+}  // extern "C"

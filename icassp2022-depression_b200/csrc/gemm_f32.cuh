@@ -1,0 +1,30 @@
+// gemm_f32.cuh — interface of the fp32 time-parallel GEMMs (input projection K1, wgrad/dgrad K6).
+#pragma once
+#include "common.cuh"
+
+namespace b200rnn {
+
+// C(m,n) (+)= sum_k A(m,k) * B(k,n) + bias1[n] + (n < bias2_n ? bias2[n] : 0)
+struct GemmParams {
+  const float* A;
+  RowMap a_rows;  // a_kcontig: row index = m (k contiguous); else row index = k (m contiguous)
+  int a_kcontig;
+  const float* B;
+  RowMap b_rows;  // b_kcontig: row index = n (k contiguous); else row index = k (n contiguous)
+  int b_kcontig;
+  float* C;
+  RowMap c_rows;  // row index = m, n contiguous
+  int M, N, K;
+  const float* bias1;
+  const float* bias2;
+  int bias2_n;
+  int accumulate;
+};
+
+// bytes of scratch launch_gemm may use for split-K partials for this problem (0 if none wanted)
+size_t gemm_scratch_bytes(int M, int N, int K);
+
+// Enqueue on `stream`. `scratch` may be NULL (then no split-K). Returns B200RNN_* code.
+int launch_gemm(const GemmParams& p, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+
+}  // namespace b200rnn

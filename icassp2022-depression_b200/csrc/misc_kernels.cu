@@ -1,0 +1,124 @@
+// misc_kernels.cu — dropout (K7), weight transpose, bias-gradient reduction. All HBM-bound, coalesced,
+// grid sized in multiples of the SM count.
+#include "misc_kernels.cuh"
+
+namespace b200rnn {
+
+namespace {
+
+constexpr int SMS = 148;
+
+// Inter-layer dropout, nn.GRU/nn.LSTM semantics (rnn.py:857-860, :1233-1236): Bernoulli(1-p) keep mask,
+// kept values scaled by 1/(1-p). One Philox call yields the mask of 4 consecutive elements.
+__global__ void rng_setup_kernel(uint64_t* hdr, uint64_t seed, uint64_t offset, uint64_t* state_dev,
+                                 uint64_t consume) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (state_dev) {
+      seed = state_dev[0];
+      offset = state_dev[1];
+      state_dev[1] = offset + consume;
+    }
+    hdr[0] = seed;
+    hdr[1] = offset;
+  }
+}
+
+__global__ void dropout_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n, float p,
+                               float scale, const uint64_t* __restrict__ hdr, uint32_t stream_id) {
+  const uint64_t seed = hdr[0], offset = hdr[1];
+  const size_t nquad = (n + 3) / 4;
+  // keep iff u >= p where u = x * 2^-32 in [0,1)
+  const uint32_t thr = (uint32_t)fminf(p * 4294967296.0f, 4294967295.0f);
+  for (size_t qd = blockIdx.x * (size_t)blockDim.x + threadIdx.x; qd < nquad;
+       qd += (size_t)gridDim.x * blockDim.x) {
+    Philox4 r = philox4x32_10(seed, offset + qd, (uint64_t)stream_id);
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    const size_t i0 = qd * 4;
+    if (i0 + 3 < n && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0) {
+      float4 v = *reinterpret_cast<const float4*>(in + i0);
+      v.x = rr[0] >= thr ? v.x * scale : 0.f;
+      v.y = rr[1] >= thr ? v.y * scale : 0.f;
+      v.z = rr[2] >= thr ? v.z * scale : 0.f;
+      v.w = rr[3] >= thr ? v.w * scale : 0.f;
+      *reinterpret_cast<float4*>(out + i0) = v;
+    } else {
+      for (int e = 0; e < 4 && i0 + e < n; ++e) out[i0 + e] = rr[e] >= thr ? in[i0 + e] * scale : 0.f;
+    }
+  }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+  for (int tidx = blockIdx.x; tidx < tiles_c * tiles_r; tidx += gridDim.x) {
+    const int tr = tidx / tiles_c, tc = tidx - tr * tiles_c;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      int r = tr * 32 + i, c = tc * 32 + threadIdx.x;
+      tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * cols + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      int c = tc * 32 + i, r = tr * 32 + threadIdx.x;
+      if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][i];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void bias_reduce_kernel(const float* __restrict__ part, int nslices, int mode, int H, float* db_ih,
+                                   float* db_hh, int accumulate) {
+  const int G = mode == B200RNN_GRU ? 3 : 4;
+  const int GH = G * H, W = (G + 1) * H;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= GH) return;
+  float s = 0.f, sn = 0.f;
+  const bool gru_n = (mode == B200RNN_GRU) && c >= 2 * H;
+  for (int k = 0; k < nslices; ++k) {  // fixed order => deterministic
+    s += part[(size_t)k * W + c];
+    if (gru_n) sn += part[(size_t)k * W + GH + (c - 2 * H)];
+  }
+  const float hh = gru_n ? sn : s;
+  if (db_ih) db_ih[c] = accumulate ? db_ih[c] + s : s;
+  if (db_hh) db_hh[c] = accumulate ? db_hh[c] + hh : hh;
+}
+
+}  // namespace
+
+int launch_rng_setup(uint64_t* hdr, uint64_t seed, uint64_t offset, uint64_t* state_dev, uint64_t consume,
+                     cudaStream_t stream) {
+  rng_setup_kernel<<<1, 32, 0, stream>>>(hdr, seed, offset, state_dev, consume);
+  B200_CUDA_CHECK(cudaGetLastError());
+  return B200RNN_OK;
+}
+
+int launch_dropout(const float* in, float* out, size_t n, float p, const uint64_t* hdr, uint32_t stream_id,
+                   cudaStream_t stream) {
+  if (n == 0) return B200RNN_OK;
+  const float scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  size_t nquad = (n + 3) / 4;
+  int blocks = (int)((nquad + 255) / 256);
+  if (blocks > SMS * 8) blocks = SMS * 8;
+  dropout_kernel<<<blocks, 256, 0, stream>>>(in, out, n, p, scale, hdr, stream_id);
+  B200_CUDA_CHECK(cudaGetLastError());
+  return B200RNN_OK;
+}
+
+int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return B200RNN_OK;
+  int tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+  int blocks = tiles < SMS * 4 ? tiles : SMS * 4;
+  transpose_kernel<<<blocks, dim3(32, 8), 0, stream>>>(src, dst, rows, cols);
+  B200_CUDA_CHECK(cudaGetLastError());
+  return B200RNN_OK;
+}
+
+int launch_bias_reduce(const float* part, int nslices, int mode, int H, float* db_ih, float* db_hh,
+                       int accumulate, cudaStream_t stream) {
+  const int G = mode == B200RNN_GRU ? 3 : 4;
+  const int GH = G * H;
+  bias_reduce_kernel<<<(GH + 127) / 128, 128, 0, stream>>>(part, nslices, mode, H, db_ih, db_hh, accumulate);
+  B200_CUDA_CHECK(cudaGetLastError());
+  return B200RNN_OK;
+}
+
+}  // namespace b200rnn

@@ -1,0 +1,44 @@
+// rnn_kernels.cuh — host-side launch interface of the persistent recurrence kernels (K2-K5).
+#pragma once
+#include "common.cuh"
+
+namespace b200rnn {
+
+// One launch runs ALL directions of one layer: grid = D * nslices clusters of C CTAs.
+struct RecFwdParams {
+  int mode, B, T, H, D;
+  int training;              // save activated gates + hn/c for backward
+  const float* w_hh[2];      // per direction [G*H, H]
+  const float* b_hh[2];      // per direction [G*H]  (GRU: only the n third is read; r,z are pre-folded)
+  float* gates[2];           // per direction [T,B,G*H]; in: x-projection + folded biases; out: activated gates
+  float* extra[2];           // per direction [T,B,H]; GRU: W_hn h + b_hn ; LSTM: c_t   (training only)
+  float* y;                  // layer output, element (t,b,d*H+j) at t*y_st + b*y_sb + d*H + j
+  long long y_st, y_sb;
+  float* h_n;                // [D,B,H] of this layer
+  float* c_n;                // [D,B,H] of this layer (LSTM) or NULL
+};
+
+struct RecBwdParams {
+  int mode, B, T, H, D;
+  const float* w_hh_t[2];    // per direction W_hh^T, [H, G*H] row-major (transposed copy)
+  const float* gates[2];     // saved activated gates [T,B,G*H]
+  const float* extra[2];     // GRU hn / LSTM c, [T,B,H]
+  const float* y;            // this layer's forward output (h_t), strided
+  long long y_st, y_sb;
+  const float* dy;           // gradient of this layer's output, strided
+  long long dy_st, dy_sb;
+  const float* dh_n;         // [D,B,H] or NULL
+  const float* dc_n;         // [D,B,H] or NULL
+  float* dgates[2];          // out: [T,B,G*H] gradient w.r.t. the x-projection (dGi)
+  float* dghn[2];            // out (GRU only): [T,B,H] gradient w.r.t. (W_hn h + b_hn) = dn * r
+  float* dbias_part[2];      // out: [nslices][(G+1)*H] per-slice column sums (rows 0..G*H: dGi; GRU tail H: dghn)
+  int nslices_out;           // filled by the launcher
+};
+
+// number of batch slices the launcher will use for this shape (needed to size dbias_part)
+int rec_bwd_max_slices(int B);
+
+int launch_rec_fwd(const RecFwdParams& p, cudaStream_t stream);
+int launch_rec_bwd(RecBwdParams& p, cudaStream_t stream);
+
+}  // namespace b200rnn

@@ -1,0 +1,150 @@
+/*
+ * b200rnn.h — C-ABI of the B200-native GRU / (Bi)LSTM sequence-encoder library.
+ *
+ * This is the drop-in boundary for the ONE hot path of
+ * speechandlanguageprocessing/ICASSP2022-Depression: the multi-layer torch.nn.GRU /
+ * bidirectional torch.nn.LSTM forward + backward that the reference constructs at
+ *   Classification/audio_gru_whole.py:59-60      (nn.GRU 256->256, 2 layers, batch_first)
+ *   Classification/text_bilstm_whole.py:54-56    (nn.LSTM 1024->H, 2 layers, bidirectional)
+ *   Classification/fuse_net_whole.py:266-268, 281-286
+ *   Regression/audio_bilstm_perm.py:72-77, Regression/text_bilstm_perm.py:67-69,
+ *   Regression/fuse_net.py:245-247, 260-265
+ * and calls at audio_gru_whole.py:105, text_bilstm_whole.py:105, fuse_net_whole.py:347,361.
+ * The arithmetic the reference reaches lives in PyTorch (torch/nn/modules/rnn.py:1221-1224 GRU
+ * equations, :842-847 LSTM equations, :171-216 parameter order); every entry point below says
+ * which piece of that interface it replaces.
+ *
+ * Rules of the ABI:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller;
+ *   - purely stream-ordered: all work is enqueued on `stream`, no host synchronisation, no hidden
+ *     allocation on the hot path, capturable in a CUDA graph;
+ *   - int return: 0 = ok, <0 = error (message via b200rnn_last_error(), thread-local);
+ *   - fp32 everywhere ("dtype": "f32").
+ */
+#ifndef B200RNN_H_
+#define B200RNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RNN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define B200RNN_API __attribute__((visibility("default")))
+#else
+#define B200RNN_API
+#endif
+
+enum { B200RNN_GRU = 0, B200RNN_LSTM = 1 };
+
+/* error codes */
+enum {
+  B200RNN_OK = 0,
+  B200RNN_ERR_INVALID = -1,     /* bad descriptor / null pointer / misaligned buffer        */
+  B200RNN_ERR_UNSUPPORTED = -2, /* shape outside what the sm_100a kernels are built for     */
+  B200RNN_ERR_CUDA = -3         /* a CUDA runtime call failed (message has cudaGetErrorString) */
+};
+
+/* flags */
+#define B200RNN_FLAG_ACCUMULATE_GRADS 1u  /* backward: dparams += grad (else dparams = grad)          */
+#define B200RNN_FLAG_SAVE_FOR_BACKWARD 2u /* forward: keep gates / cell state / layer outputs in `reserve` */
+
+/*
+ * Problem descriptor. Mirrors the constructor arguments of torch.nn.GRU / torch.nn.LSTM
+ * (rnn.py:1212 / :833) plus the call-time batch shape.
+ */
+typedef struct b200rnn_desc {
+  int32_t mode;        /* B200RNN_GRU (gate order r,z,n) or B200RNN_LSTM (gate order i,f,g,o) */
+  int32_t batch;       /* B */
+  int32_t seq_len;     /* T */
+  int32_t input_size;  /* I  (layer-0 feature width)                                        */
+  int32_t hidden_size; /* H  (supported: 128, 256)                                          */
+  int32_t num_layers;  /* L                                                                 */
+  int32_t num_dirs;    /* D  (1, or 2 = bidirectional)                                      */
+  int32_t training;    /* 1: module is in train() mode => inter-layer dropout is applied      */
+  float dropout_p;     /* inter-layer dropout probability (rnn.py:857-860 / 1233-1236)       */
+  uint32_t flags;      /* B200RNN_FLAG_*                                                    */
+} b200rnn_desc;
+
+/* ABI version of the loaded library (== B200RNN_ABI_VERSION). */
+B200RNN_API int b200rnn_version(void);
+
+/* Last error message of the calling thread ("" if none). Never NULL. */
+B200RNN_API const char* b200rnn_last_error(void);
+
+/* Number of SMs of the current device as seen by the library (148 on B200); <0 on error. */
+B200RNN_API int b200rnn_sm_count(void);
+
+/*
+ * Bytes of the two caller-owned work buffers.
+ *   reserve : forward(training=1) writes it, backward reads it (cuDNN-style reserve space)
+ *   scratch : transient; max of what forward and backward need
+ * Both must be 256-byte aligned (torch.empty on a CUDA device is).
+ */
+B200RNN_API int b200rnn_workspace_bytes(const b200rnn_desc* desc, size_t* reserve_bytes, size_t* scratch_bytes);
+
+/*
+ * Forward pass: replaces `_VF.gru` / `_VF.lstm` behind nn.GRU.forward / nn.LSTM.forward
+ * (rnn.py:1449 / :1169) with hx = None (h0 = c0 = 0, rnn.py:1432-1440).
+ *
+ *   x         [T,B,I] addressed as x[t*x_stride_t + b*x_stride_b + i]  (feature stride 1), so both the
+ *             batch_first layout of audio_gru_whole.py:60 and the permuted NON-contiguous view of
+ *             text_bilstm_whole.py:103 are consumed in place
+ *   params    4*L*D device pointers in nn order: for layer l, direction d:
+ *             weight_ih[G*H, I_l], weight_hh[G*H, H], bias_ih[G*H], bias_hh[G*H]   (rnn.py:171-216)
+ *   y         [T,B,D*H] addressed as y[t*y_stride_t + b*y_stride_b + c]
+ *   h_n       [L*D, B, H] contiguous (layer-major, direction-minor: l0 fwd, l0 rev, l1 fwd, ...)
+ *   c_n       same shape, LSTM only (NULL for GRU)
+ *   reserve   written when flags has B200RNN_FLAG_SAVE_FOR_BACKWARD (may be NULL otherwise)
+ *   scratch   required when nothing is saved (inference, or the no_grad forward of
+ *             fuse_net_whole.py:337 which still runs train-mode dropout)
+ *   dropout_seed / dropout_offset / rng_state : Philox4x32-10 key / counter base of the inter-layer
+ *             dropout mask. If rng_state (DEVICE pointer to {seed, offset}) is non-NULL the pair is read
+ *             from it on the device and the offset is advanced there, so a captured CUDA graph draws a
+ *             fresh mask at every replay; otherwise the by-value pair is used. The pair actually used is
+ *             recorded in `reserve` for b200rnn_backward.
+ */
+B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_t x_stride_t,
+                                int64_t x_stride_b, const float* const* params, float* y, int64_t y_stride_t,
+                                int64_t y_stride_b, float* h_n, float* c_n, void* reserve, void* scratch,
+                                uint64_t dropout_seed, uint64_t dropout_offset, uint64_t* rng_state,
+                                void* stream /* cudaStream_t */);
+
+/*
+ * Backward pass (BPTT): what autograd runs for loss.backward() through nn.GRU / nn.LSTM
+ * (audio_gru_whole.py:190, text_bilstm_whole.py:182). `desc` must equal the forward's.
+ *
+ *   y, dy     forward output and its gradient, strided like y above (dy has its own strides)
+ *   dh_n,dc_n gradients w.r.t. h_n / c_n, [L*D,B,H] contiguous, or NULL (= zero)
+ *   dx        [T,B,I] strided like x, or NULL to skip (the reference asks for it:
+ *             audio_gru_whole.py:179 sets requires_grad=True on the input)
+ *   dparams   4*L*D device pointers shaped like params (e.g. views into ONE flat gradient bucket that
+ *             a single ncclAllReduce consumes); entries may be NULL to skip; written or accumulated per
+ *             B200RNN_FLAG_ACCUMULATE_GRADS
+ */
+B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64_t x_stride_t,
+                                 int64_t x_stride_b, const float* const* params, const float* y,
+                                 int64_t y_stride_t, int64_t y_stride_b, const float* dy, int64_t dy_stride_t,
+                                 int64_t dy_stride_b, const float* dh_n, const float* dc_n, const void* reserve,
+                                 void* scratch, float* dx, int64_t dx_stride_t, int64_t dx_stride_b,
+                                 float* const* dparams, void* stream /* cudaStream_t */);
+
+/*
+ * Dense helper used by the path (time-parallel input projection, wgrad, dgrad):
+ *   C[m,n] (+)= sum_k A(m,k) * B(k,n) + bias[n]
+ * exposed so the parity tests can pin the GEMM on its own.
+ *   a_kcontig : 1 -> A is [M,K] row-major with leading dimension lda; 0 -> A is [K,M] row-major (lda)
+ *   b_kcontig : 1 -> B is [N,K] row-major (ldb) ("NT");               0 -> B is [K,N] row-major (ldb)
+ */
+B200RNN_API int b200rnn_gemm_f32(int M, int N, int K, const float* A, int64_t lda, int a_kcontig, const float* B,
+                     int64_t ldb, int b_kcontig, float* C, int64_t ldc, const float* bias, int accumulate,
+                     void* scratch, size_t scratch_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RNN_H_ */

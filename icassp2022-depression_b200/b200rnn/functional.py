@@ -210,13 +210,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kcontig: bool = True, b_kcontig:
     N = b.shape[0] if b_kcontig else b.shape[1]
     Kb = b.shape[1] if b_kcontig else b.shape[0]
     assert K == Kb, (a.shape, b.shape)
-    assert a.stride(1) == 1 and b.stride(1) == 1
+    assert (a.stride(1) == 1 or a.size(1) == 1) and (b.stride(1) == 1 or b.size(1) == 1)
+    lda = a.stride(0) if a.size(1) > 1 else 1
+    ldb = b.stride(0) if b.size(1) > 1 else 1
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
         assert not accumulate
     sbytes = M * N * 4 * 64 if use_splitk else 0
     scratch = torch.empty(sbytes, dtype=torch.uint8, device=a.device) if sbytes else None
-    rc = lib.b200rnn_gemm_f32(M, N, K, a.data_ptr(), a.stride(0), int(a_kcontig), b.data_ptr(), b.stride(0),
+    rc = lib.b200rnn_gemm_f32(M, N, K, a.data_ptr(), lda, int(a_kcontig), b.data_ptr(), ldb,
                               int(b_kcontig), out.data_ptr(), out.stride(0),
                               bias.data_ptr() if bias is not None else None, int(accumulate),
                               scratch.data_ptr() if scratch is not None else None, sbytes, _stream_ptr())

@@ -9,10 +9,11 @@ from ._lib import B200RNNError
 from .modules import GRU, LSTM, from_torch, install, uninstall
 from .functional import RNNConfig, gemm, rnn_forward
 from .staging import FuseBatch, PinnedStager, stage_fuse_batch
+from .dp import GradBucket, broadcast_parameters, shard_batch
 from .models import AudioBiLSTM, MyLoss, TextBiLSTM, attention_pool, fusion_net
 
 __all__ = [
     "GRU", "LSTM", "install", "uninstall", "from_torch", "rnn_forward", "gemm", "RNNConfig", "B200RNNError",
     "AudioBiLSTM", "TextBiLSTM", "fusion_net", "MyLoss", "attention_pool", "FuseBatch", "PinnedStager",
-    "stage_fuse_batch",
+    "stage_fuse_batch", "GradBucket", "broadcast_parameters", "shard_batch",
 ]

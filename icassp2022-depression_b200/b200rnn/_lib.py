@@ -22,10 +22,13 @@ SYMBOLS = (
     "b200rnn_version",
     "b200rnn_last_error",
     "b200rnn_sm_count",
+    "b200rnn_launch_count",
     "b200rnn_workspace_bytes",
     "b200rnn_forward",
     "b200rnn_backward",
     "b200rnn_gemm_f32",
+    "b200rnn_profile",
+    "b200rnn_profile_read",
 )
 
 
@@ -72,6 +75,8 @@ def load() -> ctypes.CDLL:
     lib.b200rnn_version.argtypes = []
     lib.b200rnn_last_error.restype = c_char_p
     lib.b200rnn_last_error.argtypes = []
+    lib.b200rnn_launch_count.restype = ctypes.c_ulonglong
+    lib.b200rnn_launch_count.argtypes = []
     lib.b200rnn_sm_count.restype = c_int
     lib.b200rnn_sm_count.argtypes = []
     lib.b200rnn_workspace_bytes.restype = c_int
@@ -103,6 +108,10 @@ def load() -> ctypes.CDLL:
         c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p,
         c_int, c_void_p, c_size_t, c_void_p,
     ]
+    lib.b200rnn_profile.restype = c_int
+    lib.b200rnn_profile.argtypes = [c_int]
+    lib.b200rnn_profile_read.restype = c_int
+    lib.b200rnn_profile_read.argtypes = [c_int, POINTER(c_float), POINTER(c_int)]
     del fp
     v = lib.b200rnn_version()
     if v != ABI_VERSION:
@@ -128,3 +137,21 @@ def ptr_array(ptrs) -> ctypes.Array:
     for i, p in enumerate(ptrs):
         arr[i] = p
     return arr
+
+
+PROF_REC_FWD, PROF_REC_BWD, PROF_GEMM, PROF_MISC = 0, 1, 2, 3
+
+
+def profile(enable: bool) -> None:
+    check(load().b200rnn_profile(1 if enable else 0), "profile")
+
+
+def profile_read(kind: int) -> tuple[float, int]:
+    """(total milliseconds, launches) of the library's launches of ``kind`` since profiling was enabled."""
+    ms, n = c_float(0.0), c_int(0)
+    check(load().b200rnn_profile_read(kind, ctypes.byref(ms), ctypes.byref(n)), "profile_read")
+    return float(ms.value), int(n.value)
+
+
+def launch_count() -> int:
+    return int(load().b200rnn_launch_count())

@@ -1,0 +1,84 @@
+"""Batch-sharded data parallelism for the path: one process per GPU, the model replicated,
+sequences sharded over ranks, and exactly ONE all-reduce per step over a single flat fp32 gradient bucket.
+
+The reference has no distributed code at all; this is the one parallel axis the hot path offers (independent
+sequences). Gradients of every trainable parameter are views into one contiguous buffer: the wgrad GEMMs of the
+B200 GRU/LSTM write straight into those views (``B200RNN_FLAG_ACCUMULATE_GRADS``), PyTorch's autograd accumulates
+the dense shells' gradients into them in place, and ``all_reduce`` consumes the buffer as is — no pack kernel.
+Backend: NCCL over NVLink 5 / NVSwitch on the GPU box, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .modules import _B200RNNBase
+
+
+class GradBucket:
+    """Flat gradient bucket over the trainable parameters of ``model``."""
+
+    def __init__(self, model: torch.nn.Module, process_group: Optional[dist.ProcessGroup] = None,
+                 direct_rnn_grads: bool = True):
+        self.params: List[torch.nn.Parameter] = [p for p in model.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradBucket: the model has no trainable parameter")
+        dev = self.params[0].device
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self._views = {}
+        off = 0
+        for p in self.params:
+            v = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            p.grad = v                      # autograd accumulates into this view in place
+            self._views[p.data_ptr()] = v      # keyed by storage address: saved tensors may be re-wrapped
+        if direct_rnn_grads:
+            for m in model.modules():
+                if isinstance(m, _B200RNNBase):
+                    m._grad_sink = self._sink
+
+    # called from the RNN autograd function: where should the weight gradients be accumulated?
+    def _sink(self, weights: Iterable[torch.Tensor]):
+        return [self._views.get(w.data_ptr()) for w in weights]
+
+    @property
+    def nbytes(self) -> int:
+        return self.numel * 4
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def allreduce(self, average: bool = True) -> None:
+        """The step's single collective. ``average`` gives mean-reduced-loss semantics across shards."""
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            if average:
+                self.flat.mul_(1.0 / self.world)
+
+
+def broadcast_parameters(model: torch.nn.Module, src: int = 0,
+                         process_group: Optional[dist.ProcessGroup] = None) -> None:
+    """Make every replica start from rank ``src``'s weights (one flat broadcast)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(process_group) == 1:
+        return
+    tensors = [p.data for p in model.parameters()] + [b.data for b in model.buffers() if b.dtype.is_floating_point]
+    if not tensors:
+        return
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.broadcast(flat, src=src, group=process_group)
+    off = 0
+    for t in tensors:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+
+
+def shard_batch(n_global: int, rank: int, world: int) -> slice:
+    """Rows of the global batch owned by ``rank`` (contiguous, sizes differ by at most one)."""
+    base, rem = divmod(n_global, world)
+    start = rank * base + min(rank, rem)
+    return slice(start, start + base + (1 if rank < rem else 0))

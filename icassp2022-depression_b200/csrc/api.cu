@@ -5,6 +5,7 @@
 //                       -> [K7 dropout, train mode, not after the last layer]
 // Per layer, backward:  [W_hh transpose per direction] -> [one persistent BPTT launch, all directions]
 //                       -> [bias reduce, wgrad GEMMs (split-K, deterministic), dgrad GEMM]
+#include <atomic>
 #include <mutex>
 #include <stdarg.h>
 #include <string.h>
@@ -16,6 +17,9 @@
 namespace b200rnn {
 
 static thread_local char g_err[512] = {0};
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -168,6 +172,8 @@ extern "C" {
 B200RNN_API int b200rnn_version(void) { return B200RNN_ABI_VERSION; }
 
 B200RNN_API const char* b200rnn_last_error(void) { return g_err; }
+
+B200RNN_API unsigned long long b200rnn_launch_count(void) { return g_launches.load(); }
 
 B200RNN_API int b200rnn_sm_count(void) {
   int dev = 0, n = 0;

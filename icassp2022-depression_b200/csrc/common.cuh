@@ -10,6 +10,7 @@ namespace b200rnn {
 
 // ---- error plumbing (thread-local message, int codes across the C ABI) -------------------------
 void set_error(const char* fmt, ...);
+void count_launch(int n = 1);  // bumps the counter behind b200rnn_launch_count()
 #define B200_CUDA_CHECK(expr)                                                                      \
   do {                                                                                             \
     cudaError_t _e = (expr);                                                                       \

@@ -6,6 +6,7 @@
 // fp32 FFMA on purpose: the reference path is fp32 (torch rnn.py:1221-1224, :842-847) and parity is
 // judged at 1e-5; a 3xTF32 tcgen05 variant is the planned replacement for the dense shapes.
 #include "gemm_f32.cuh"
+#include "profile.cuh"
 
 namespace b200rnn {
 
@@ -285,12 +286,14 @@ int launch_gemm(const GemmParams& p, void* scratch, size_t scratch_bytes, cudaSt
     d.splitk = 1;
     d.k_chunk = BK;
   }
+  ProfScope prof(PROF_GEMM, stream);
   dim3 grid((p.N + pl.tile - 1) / pl.tile, (p.M + pl.tile - 1) / pl.tile, d.splitk);
   if (pl.tile == 128)
     launch_tile<128, 128>(d, p.a_kcontig, p.b_kcontig, grid, stream);
   else
     launch_tile<64, 64>(d, p.a_kcontig, p.b_kcontig, grid, stream);
   B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   if (d.splitk > 1) {
     size_t total = (size_t)p.M * p.N;
     int blocks = (int)((total + 255) / 256);
@@ -298,6 +301,7 @@ int launch_gemm(const GemmParams& p, void* scratch, size_t scratch_bytes, cudaSt
     splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(d.partial, d.splitk, p.M, p.N, p.C, p.c_rows, p.bias1,
                                                      p.bias2, p.bias2_n, p.accumulate);
     B200_CUDA_CHECK(cudaGetLastError());
+    count_launch();
   }
   return B200RNN_OK;
 }

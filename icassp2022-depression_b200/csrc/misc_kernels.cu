@@ -88,6 +88,7 @@ int launch_rng_setup(uint64_t* hdr, uint64_t seed, uint64_t offset, uint64_t* st
                      cudaStream_t stream) {
   rng_setup_kernel<<<1, 32, 0, stream>>>(hdr, seed, offset, state_dev, consume);
   B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return B200RNN_OK;
 }
 
@@ -100,6 +101,7 @@ int launch_dropout(const float* in, float* out, size_t n, float p, const uint64_
   if (blocks > SMS * 8) blocks = SMS * 8;
   dropout_kernel<<<blocks, 256, 0, stream>>>(in, out, n, p, scale, hdr, stream_id);
   B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return B200RNN_OK;
 }
 
@@ -109,6 +111,7 @@ int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStrea
   int blocks = tiles < SMS * 4 ? tiles : SMS * 4;
   transpose_kernel<<<blocks, dim3(32, 8), 0, stream>>>(src, dst, rows, cols);
   B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return B200RNN_OK;
 }
 
@@ -118,6 +121,7 @@ int launch_bias_reduce(const float* part, int nslices, int mode, int H, float* d
   const int GH = G * H;
   bias_reduce_kernel<<<(GH + 127) / 128, 128, 0, stream>>>(part, nslices, mode, H, db_ih, db_hh, accumulate);
   B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return B200RNN_OK;
 }
 

@@ -18,6 +18,9 @@
 //
 // fp32 FFMA by choice: the per-step contraction is [BS x H] x [H x G*HS] with BS = 2..8 rows per CTA —
 // far too skinny for tcgen05 tiles, and parity is judged at 1e-5 against an fp32 reference.
+#include <mutex>
+
+#include "profile.cuh"
 #include "ptx.cuh"
 #include "rnn_core.cuh"
 #include "rnn_kernels.cuh"
@@ -354,8 +357,10 @@ __global__ void __launch_bounds__(BwdCfg<MODE, H, C, BS, UPW>::NT, 1)
 // =================================================================================================
 template <typename K>
 int prepare_kernel(K kernel, size_t smem) {
-  static thread_local const void* done[64];
-  static thread_local int ndone = 0;
+  static std::mutex mu;  // forward and autograd-backward threads both launch
+  static const void* done[64];
+  static int ndone = 0;
+  std::lock_guard<std::mutex> lk(mu);
   for (int i = 0; i < ndone; ++i)
     if (done[i] == (const void*)kernel) return B200RNN_OK;
   B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -365,9 +370,10 @@ int prepare_kernel(K kernel, size_t smem) {
 
 template <typename K, typename P>
 int launch_clustered(K kernel, const P& params, int nslices, int nclusters, int C, int NT, size_t smem,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int prof_kind) {
   int rc = prepare_kernel(kernel, smem);
   if (rc) return rc;
+  ProfScope prof(prof_kind, stream);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclusters * C), 1, 1);
   cfg.blockDim = dim3((unsigned)NT, 1, 1);
@@ -381,6 +387,7 @@ int launch_clustered(K kernel, const P& params, int nslices, int nclusters, int 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, params, nslices));
+  count_launch();
   return B200RNN_OK;
 }
 
@@ -391,8 +398,10 @@ int max_active_clusters(K kernel, int C, int NT, size_t smem) {
     const void* k;
     int n;
   };
-  static thread_local Entry cache[64];
-  static thread_local int ncache = 0;
+  static std::mutex mu;
+  static Entry cache[64];
+  static int ncache = 0;
+  std::lock_guard<std::mutex> lk(mu);
   for (int i = 0; i < ncache; ++i)
     if (cache[i].k == (const void*)kernel) return cache[i].n;
   if (prepare_kernel(kernel, smem) != B200RNN_OK) return 0;
@@ -423,7 +432,7 @@ bool try_fwd(const RecFwdParams& p, cudaStream_t s, bool force, int* rc) {
   const int nslices = (p.B + BS - 1) / BS;
   const int nclusters = nslices * p.D;
   if (!force && nclusters > max_active_clusters(k, C, Cfg::NT, Cfg::SMEM)) return false;
-  *rc = launch_clustered(k, p, nslices, nclusters, C, Cfg::NT, Cfg::SMEM, s);
+  *rc = launch_clustered(k, p, nslices, nclusters, C, Cfg::NT, Cfg::SMEM, s, PROF_REC_FWD);
   return true;
 }
 
@@ -435,7 +444,7 @@ bool try_bwd(RecBwdParams& p, cudaStream_t s, bool force, int* rc) {
   const int nclusters = nslices * p.D;
   if (!force && nclusters > max_active_clusters(k, C, Cfg::NT, Cfg::SMEM)) return false;
   p.nslices_out = nslices;
-  *rc = launch_clustered(k, p, nslices, nclusters, C, Cfg::NT, Cfg::SMEM, s);
+  *rc = launch_clustered(k, p, nslices, nclusters, C, Cfg::NT, Cfg::SMEM, s, PROF_REC_BWD);
   return true;
 }
 

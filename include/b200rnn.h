@@ -76,6 +76,9 @@ B200RNN_API int b200rnn_version(void);
 /* Last error message of the calling thread ("" if none). Never NULL. */
 B200RNN_API const char* b200rnn_last_error(void);
 
+/* Kernels this library has launched in this process so far (captured launches count once per capture). */
+B200RNN_API unsigned long long b200rnn_launch_count(void);
+
 /* Number of SMs of the current device as seen by the library (148 on B200); <0 on error. */
 B200RNN_API int b200rnn_sm_count(void);
 
@@ -143,6 +146,16 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
 B200RNN_API int b200rnn_gemm_f32(int M, int N, int K, const float* A, int64_t lda, int a_kcontig, const float* B,
                      int64_t ldb, int b_kcontig, float* C, int64_t ldc, const float* bias, int accumulate,
                      void* scratch, size_t scratch_bytes, void* stream);
+
+/*
+ * Optional device-side timing of the library's own launches (CUDA event pairs on the launching stream),
+ * used by bench.py for the roofline figure. kind: 0 = forward recurrence, 1 = backward recurrence,
+ * 2 = GEMM, 3 = other. Do not enable while capturing a CUDA graph.
+ *   b200rnn_profile(enable)       : switch on/off and forget what was recorded so far
+ *   b200rnn_profile_read(kind,..) : wait for the recorded launches of `kind`; sum of their durations + count
+ */
+B200RNN_API int b200rnn_profile(int enable);
+B200RNN_API int b200rnn_profile_read(int kind, float* total_ms, int* launches);
 
 #ifdef __cplusplus
 }

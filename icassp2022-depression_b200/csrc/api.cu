@@ -356,9 +356,8 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
         set_error("backward: null parameter pointer (layer %d dir %d)", l, k);
         return B200RNN_ERR_INVALID;
       }
-      rc = launch_transpose(pp[1], S + sl.b_wt[k], (int)d.GH, d.H, st);  // W_hh [GH,H] -> [H,GH]
-      if (rc) return rc;
-      bp.w_hh_t[k] = S + sl.b_wt[k];
+      bp.w_hh[k] = pp[1];
+      bp.w_prep[k] = S + sl.b_wt[k];
       bp.gates[k] = R + rl.gates[l][k];
       bp.extra[k] = R + rl.extra[l][k];
       bp.dgates[k] = S + sl.b_dgates[k];

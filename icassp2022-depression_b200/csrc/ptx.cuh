@@ -82,5 +82,16 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, float4 v) {
                : "memory");
 }
 
+// st.async: 16-byte store into a peer CTA's shared memory that also completes 16 bytes of the transaction
+// count of an mbarrier in THAT CTA — data and signal travel together, no fence / cluster barrier needed.
+// Both addresses are shared::cluster addresses (mapa) of the same target CTA.
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, float4 v, uint32_t cluster_mbar) {
+  asm volatile(
+      "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+          cluster_addr),
+      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(cluster_mbar)
+      : "memory");
+}
+
 }  // namespace ptx
 }  // namespace b200rnn

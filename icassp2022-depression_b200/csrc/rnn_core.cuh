@@ -1,17 +1,20 @@
 // rnn_core.cuh — the per-step contraction shared by the persistent forward and backward kernels.
 //
-// One warp owns NR*UPW rows of a shared-memory resident weight slice (row-major, length KLEN) and
-// multiplies them with BS vectors of length KLEN that also sit in shared memory. The contraction
-// dimension is spread across the 32 lanes (each lane owns 4 consecutive k per 128-wide chunk, so all
-// shared-memory reads are conflict-free 16-byte loads), and the cross-lane sum is a transposing
-// butterfly: every stage halves the number of live partial sums per lane, so the whole reduction costs
-// about one SHFL+FADD per accumulator instead of five.
+// A warp multiplies UPW = CL*UPL rows of a weight slice (row-major, length KLEN) per row-group with BS vectors
+// of length KLEN that sit in shared memory. Its 32 lanes form a CL x KL grid: the KL "k-lanes" split the
+// contraction dimension (each owns 4 consecutive k per 4*KL-wide chunk, so every shared-memory read is a
+// conflict-free 16-byte load), the CL "column-lanes" own different rows. The cross-lane sum over the KL lanes is
+// a transposing butterfly: every stage halves the number of live partial sums per lane (UPL*BS == KL, so exactly
+// one sum per row-group is left per lane), i.e. about one SHFL+FADD per accumulator instead of log2(KL).
 //
 // To keep every register index static, the *data* a register slot holds is permuted per lane:
-//   slot (au, ab) of lane L accumulates   unit  = au ^ p(L),  batch = ab ^ q(L)
-// with p = the top log2(UPW) lane bits and q = the next log2(BS) lane bits. Row / vector addresses are
-// computed per lane (free: rows differ by multiples of KLEN floats, i.e. the same banks), and each
-// butterfly stage becomes "slot[i] += shfl_xor(slot[i + half])" with compile-time i.
+//   slot (au, ab) of k-lane kl accumulates   unit = au ^ p(kl),  batch = ab ^ q(kl)
+// with p = the top log2(UPL) bits of kl and q = its low log2(BS) bits. Row / vector addresses are computed per
+// lane (free: rows differ by multiples of KLEN floats, i.e. the same banks), and each butterfly stage becomes
+// "slot[i] += shfl_xor(slot[i + half])" with compile-time i.
+//
+// The last RG row-groups can be register resident (loaded once per kernel): they cost no shared-memory
+// bandwidth in the time loop, which is what bounds the loop once the FFMA pipe is fed.
 #pragma once
 #include "common.cuh"
 
@@ -26,49 +29,93 @@ struct Log2<1> {
   static constexpr int value = 0;
 };
 
-template <int UPW, int BS>
+template <int KL, int UPL, int BS>
 struct LaneMap {
-  static constexpr int LU = Log2<UPW>::value;
+  static constexpr int LK = Log2<KL>::value;
+  static constexpr int LU = Log2<UPL>::value;
   static constexpr int LB = Log2<BS>::value;
-  static_assert((1 << LU) == UPW && (1 << LB) == BS, "UPW and BS must be powers of two");
-  static_assert(LU + LB <= 5, "UPW*BS must be <= 32");
-  static constexpr int NREP = 1 << (5 - LU - LB);  // lanes holding the same (unit,batch) result
-  __device__ static __forceinline__ int p(int lane) { return lane >> (5 - LU); }
-  __device__ static __forceinline__ int q(int lane) { return (lane >> (5 - LU - LB)) & (BS - 1); }
-  __device__ static __forceinline__ int rep(int lane) { return lane & (NREP - 1); }
+  static_assert((1 << LK) == KL && (1 << LU) == UPL && (1 << LB) == BS, "KL, UPL, BS must be powers of two");
+  static_assert(UPL * BS == KL && KL <= 32, "one reduced value per lane needs UPL*BS == KL <= 32");
+  static constexpr int CL = 32 / KL;     // column-lanes
+  static constexpr int UPW = CL * UPL;   // rows (units) per warp and row-group
+  __device__ static __forceinline__ int kl(int lane) { return lane & (KL - 1); }
+  __device__ static __forceinline__ int cl(int lane) { return lane >> LK; }
+  __device__ static __forceinline__ int p(int lane) { return kl(lane) >> LB; }
+  __device__ static __forceinline__ int q(int lane) { return lane & (BS - 1); }
+  // unit (within the warp) and batch (within the slice) this lane owns after the butterfly
+  __device__ static __forceinline__ int unit(int lane) { return cl(lane) * UPL + p(lane); }
+  // lane that owns (unit u of the warp, batch b)
+  __device__ static __forceinline__ int lane_of(int u, int b) {
+    return ((u >> LU) << LK) | ((u & (UPL - 1)) << LB) | b;
+  }
 };
 
-// acc[r][au][ab] += sum_k W[row(r, au^p)][k] * vec[ab^q][k]   over this lane's k (partial sums)
-//   W_s   : weight slice, row-major [.][KLEN]
-//   row0  : first row of this warp inside group r is  r*group_stride + row0 + unit
+// Load the register-resident row-groups: wreg[r][au][e] for k = chunk*4*KL + kl*4 + (e&3).
+//   Wg : global weight matrix, row-major with leading dimension KLEN; row of (group r, unit u) = grow0 + r*gstride + u
+template <int RG, int KL, int UPL, int BS, int KLEN>
+__device__ __forceinline__ void load_resident(const float* __restrict__ Wg, long long gstride_rows, long long grow0,
+                                              int lane, float (&wreg)[RG > 0 ? RG : 1][UPL][KLEN / KL]) {
+  using LM = LaneMap<KL, UPL, BS>;
+  const int kl = LM::kl(lane), p = LM::p(lane), c = LM::cl(lane);
+#pragma unroll
+  for (int r = 0; r < RG; ++r)
+#pragma unroll
+    for (int au = 0; au < UPL; ++au) {
+      const float* row = Wg + (grow0 + (long long)r * gstride_rows + c * UPL + (au ^ p)) * KLEN;
+#pragma unroll
+      for (int i = 0; i < KLEN / (4 * KL); ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row + i * 4 * KL + kl * 4));
+        wreg[r][au][i * 4 + 0] = v.x;
+        wreg[r][au][i * 4 + 1] = v.y;
+        wreg[r][au][i * 4 + 2] = v.z;
+        wreg[r][au][i * 4 + 3] = v.w;
+      }
+    }
+}
+
+// acc[r][au][ab] = sum over this lane's k of  W[row(r, au^p)][k] * vec[ab^q][k]      (partial sums)
+//   W_s   : shared-memory weight slice holding the first NR-RG row-groups, row-major [.][KLEN];
+//           row of (group r, unit u of this warp) = r*group_stride + row0 + u
+//   wreg  : the last RG row-groups, register resident (see load_resident)
 //   vec_s : [BS][KLEN]
-template <int NR, int UPW, int BS, int KLEN>
+//   VSTRIDE : floats between consecutive batch rows of vec_s;  ZERO : start from 0 (else accumulate)
+template <int NR, int RG, int KL, int UPL, int BS, int KLEN, int VSTRIDE = KLEN, bool ZERO = true>
 __device__ __forceinline__ void warp_partial_dots(const float* __restrict__ W_s, int group_stride, int row0,
+                                                  const float (&wreg)[RG > 0 ? RG : 1][UPL][KLEN / KL],
                                                   const float* __restrict__ vec_s, int lane,
-                                                  float (&acc)[NR][UPW][BS]) {
-  using LM = LaneMap<UPW, BS>;
-  static_assert(KLEN % 128 == 0, "contraction length must be a multiple of 128");
-  const int p = LM::p(lane), q = LM::q(lane);
+                                                  float (&acc)[NR][UPL][BS]) {
+  using LM = LaneMap<KL, UPL, BS>;
+  static_assert(KLEN % (4 * KL) == 0, "contraction length must be a multiple of 4*KL");
+  const int kl = LM::kl(lane), p = LM::p(lane), q = LM::q(lane), c = LM::cl(lane);
+  if (ZERO) {
 #pragma unroll
-  for (int r = 0; r < NR; ++r)
+    for (int r = 0; r < NR; ++r)
 #pragma unroll
-    for (int au = 0; au < UPW; ++au)
+      for (int au = 0; au < UPL; ++au)
 #pragma unroll
-      for (int ab = 0; ab < BS; ++ab) acc[r][au][ab] = 0.f;
+        for (int ab = 0; ab < BS; ++ab) acc[r][au][ab] = 0.f;
+  }
 
 #pragma unroll
-  for (int i = 0; i < KLEN / 128; ++i) {
-    const int koff = i * 128 + lane * 4;
+  for (int i = 0; i < KLEN / (4 * KL); ++i) {
+    const int koff = i * 4 * KL + kl * 4;
     float4 hv[BS];
 #pragma unroll
     for (int ab = 0; ab < BS; ++ab)
-      hv[ab] = *reinterpret_cast<const float4*>(&vec_s[(ab ^ q) * KLEN + koff]);
+      hv[ab] = *reinterpret_cast<const float4*>(&vec_s[(ab ^ q) * VSTRIDE + koff]);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
 #pragma unroll
-      for (int au = 0; au < UPW; ++au) {
-        const int row = r * group_stride + row0 + (au ^ p);
-        const float4 wv = *reinterpret_cast<const float4*>(&W_s[row * KLEN + koff]);
+      for (int au = 0; au < UPL; ++au) {
+        float4 wv;
+        if (r < NR - RG) {
+          const int row = r * group_stride + row0 + c * UPL + (au ^ p);
+          wv = *reinterpret_cast<const float4*>(&W_s[row * KLEN + koff]);
+        } else {
+          const int ri = (r - (NR - RG)) > 0 ? (r - (NR - RG)) : 0;
+          wv = make_float4(wreg[ri][au][i * 4 + 0], wreg[ri][au][i * 4 + 1], wreg[ri][au][i * 4 + 2],
+                           wreg[ri][au][i * 4 + 3]);
+        }
 #pragma unroll
         for (int ab = 0; ab < BS; ++ab) {
           float a = acc[r][au][ab];
@@ -83,16 +130,16 @@ __device__ __forceinline__ void warp_partial_dots(const float* __restrict__ W_s,
   }
 }
 
-// Transposing butterfly. On return acc[r][0][0] of lane L holds the full sum for
-// unit p(L), batch q(L) (replicated over the NREP low lanes).
-template <int NR, int UPW, int BS>
-__device__ __forceinline__ void warp_transpose_reduce(float (&acc)[NR][UPW][BS]) {
+// Transposing butterfly over the KL k-lanes. On return acc[r][0][0] of a lane holds the full sum for
+// unit LaneMap::unit(lane), batch LaneMap::q(lane).
+template <int NR, int KL, int UPL, int BS>
+__device__ __forceinline__ void warp_transpose_reduce(float (&acc)[NR][UPL][BS]) {
   constexpr unsigned FULL = 0xffffffffu;
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
-    int off = 16;
+    int off = KL / 2;
 #pragma unroll
-    for (int s = UPW / 2; s >= 1; s >>= 1) {
+    for (int s = UPL / 2; s >= 1; s >>= 1) {
 #pragma unroll
       for (int au = 0; au < s; ++au)
 #pragma unroll
@@ -105,8 +152,6 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&acc)[NR][UPW][BS])
       for (int ab = 0; ab < s; ++ab) acc[r][0][ab] += __shfl_xor_sync(FULL, acc[r][0][ab + s], off);
       off >>= 1;
     }
-#pragma unroll
-    for (; off >= 1; off >>= 1) acc[r][0][0] += __shfl_xor_sync(FULL, acc[r][0][0], off);
   }
 }
 

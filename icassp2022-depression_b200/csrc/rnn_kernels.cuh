@@ -20,7 +20,8 @@ struct RecFwdParams {
 
 struct RecBwdParams {
   int mode, B, T, H, D;
-  const float* w_hh_t[2];    // per direction W_hh^T, [H, G*H] row-major (transposed copy)
+  const float* w_hh[2];      // per direction weight_hh [G*H, H]
+  float* w_prep[2];          // per direction scratch, G*H*H floats: per-CTA transposed slices (filled by the launcher)
   const float* gates[2];     // saved activated gates [T,B,G*H]
   const float* extra[2];     // GRU hn / LSTM c, [T,B,H]
   const float* y;            // this layer's forward output (h_t), strided

@@ -6,19 +6,21 @@
 //
 // Design (one launch = every time step of every direction of one layer):
 //   * grid = D * nslices thread-block clusters of C CTAs. A cluster owns BS batch rows; CTA `rank` of the
-//     cluster owns HS = H/C hidden units and keeps the matching rows of W_hh (forward) or of W_hh^T
-//     (backward) resident in shared memory for the whole sequence. The slice is staged once with TMA bulk
-//     copies (cp.async.bulk ... mbarrier::complete_tx) straight from the parameter tensor.
+//     cluster owns HS = H/C hidden units and keeps the matching rows of W_hh (forward) or columns of W_hh
+//     (backward) on chip for the whole sequence: G-RG gate blocks in shared memory, staged once with TMA bulk
+//     copies (cp.async.bulk ... mbarrier::complete_tx), and RG gate blocks in registers.
 //   * per step every warp contracts its rows against the BS state vectors (rnn_core.cuh: K across lanes,
-//     transposing shuffle butterfly), the lane that ends up owning (unit, batch) applies the gate
-//     non-linearities and the state update in registers, and the new state slice is all-gathered into the
-//     C peer CTAs with st.shared::cluster (DSMEM), double buffered, one cluster barrier per step
-//     (arrive.release early, wait.acquire after the global stores / next-step prefetch).
+//     transposing shuffle butterfly); the lane that ends up owning (unit, batch) applies the gate
+//     non-linearities and the state update in registers.
+//   * the new state slice is all-gathered into the C peer CTAs with st.async (16-byte DSMEM stores that complete
+//     transaction bytes on an mbarrier in the destination CTA): data and "ready" signal travel together, the
+//     consumer waits on a local mbarrier, double buffered. No cluster barrier, fence or L1 flush in the loop.
 //   * batch slices are independent clusters: no grid-wide synchronisation anywhere.
 //
-// fp32 FFMA by choice: the per-step contraction is [BS x H] x [H x G*HS] with BS = 2..8 rows per CTA —
+// fp32 FFMA by choice: the per-step contraction is [BS x H] x [H x G*HS] with BS = 4..8 rows per CTA —
 // far too skinny for tcgen05 tiles, and parity is judged at 1e-5 against an fp32 reference.
 #include <mutex>
+#include <stdlib.h>
 
 #include "profile.cuh"
 #include "ptx.cuh"
@@ -30,48 +32,68 @@ namespace b200rnn {
 namespace {
 
 constexpr int MAX_SMEM = 232448;  // 227 KB opt-in limit per CTA on sm_100
+constexpr unsigned FULLMASK = 0xffffffffu;
 
-template <int MODE, int H, int C, int BS, int UPW>
-struct FwdCfg {
-  static constexpr int G = (MODE == B200RNN_GRU) ? 3 : 4;
-  static constexpr int HS = H / C;
-  static constexpr int NW = HS / UPW;
-  static constexpr int NT = NW * 32;
-  static constexpr int NCOL = G * HS;
-  static constexpr size_t W_BYTES = (size_t)NCOL * H * sizeof(float);
-  static constexpr size_t V_BYTES = (size_t)2 * BS * H * sizeof(float);
-  static constexpr size_t SMEM = W_BYTES + V_BYTES + 16;
-  static_assert(HS * C == H && NW * UPW == HS, "bad split");
-  static_assert(NT <= 1024 && SMEM <= MAX_SMEM, "config does not fit an SM");
-};
-
-template <int MODE, int H, int C, int BS, int UPW>
-struct BwdCfg {
+template <int MODE, int H, int C, int BS, int KL, int UPL, int RG>
+struct RecCfg {
   static constexpr int G = (MODE == B200RNN_GRU) ? 3 : 4;
   static constexpr int GH = G * H;
   static constexpr int HS = H / C;
+  static constexpr int UPW = (32 / KL) * UPL;
   static constexpr int NW = HS / UPW;
   static constexpr int NT = NW * 32;
-  static constexpr size_t W_BYTES = (size_t)HS * GH * sizeof(float);
-  static constexpr size_t V_BYTES = (size_t)2 * BS * GH * sizeof(float);
-  static constexpr size_t SMEM = W_BYTES + V_BYTES + 16;
-  static_assert(HS * C == H && NW * UPW == HS, "bad split");
-  static_assert(NT <= 1024 && SMEM <= MAX_SMEM, "config does not fit an SM");
+  static constexpr int NSM = G - RG;  // gate blocks held in shared memory
+  static constexpr size_t W_BYTES = (size_t)NSM * HS * H * sizeof(float);
+  static constexpr size_t FWD_SMEM = W_BYTES + (size_t)2 * BS * H * sizeof(float) + 32;
+  static constexpr size_t BWD_SMEM = W_BYTES + (size_t)2 * BS * GH * sizeof(float) + 32;
+  static_assert(RG == 0 || RG == 1, "at most one register-resident gate block");
+  static_assert(HS * C == H && NW * UPW == HS && NW >= 1, "bad split");
+  static_assert(UPW % 4 == 0, "the exchange packs 4 units per 16-byte store");
+  static_assert(NT <= 1024, "too many threads");
 };
+
+// All-gather `val` (owned by lane (unit, batch) of every warp) into vec[b][col0 + unit] of all C CTAs:
+// 4 shuffles gather 4 consecutive units, one st.async.v4 per (destination, chunk).
+template <int C, int KL, int UPL, int BS>
+__device__ __forceinline__ void allgather_units(float val, float* vec_local, int vstride, int col0,
+                                                uint64_t* bar_local, int lane) {
+  using LM = LaneMap<KL, UPL, BS>;
+  constexpr int UPW = LM::UPW;
+  constexpr int NCH = UPW * BS / 4;  // 16-byte chunks per destination
+  constexpr int NST = C * NCH;
+  const uint32_t bar_addr = ptx::smem_u32(bar_local);
+#pragma unroll
+  for (int it = 0; it < (NST + 31) / 32; ++it) {
+    const int idx = it * 32 + lane;
+    const bool act = idx < NST;
+    const int id2 = act ? idx : 0;
+    const int r = id2 / NCH, ch = id2 % NCH;
+    const int b = ch / (UPW / 4), quad = ch % (UPW / 4);
+    float4 v;
+    v.x = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 0, b));
+    v.y = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 1, b));
+    v.z = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 2, b));
+    v.w = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 3, b));
+    if (act) {
+      const uint32_t dst = ptx::smem_u32(&vec_local[b * vstride + col0 + quad * 4]);
+      ptx::st_async_v4(ptx::mapa(dst, (uint32_t)r), v, ptx::mapa(bar_addr, (uint32_t)r));
+    }
+  }
+}
 
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int MODE, int H, int C, int BS, int UPW>
-__global__ void __launch_bounds__(FwdCfg<MODE, H, C, BS, UPW>::NT, 1)
+template <int MODE, int H, int C, int BS, int KL, int UPL, int RG>
+__global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     rec_fwd_kernel(const RecFwdParams p, const int nslices) {
-  using Cfg = FwdCfg<MODE, H, C, BS, UPW>;
-  using LM = LaneMap<UPW, BS>;
-  constexpr int G = Cfg::G, HS = Cfg::HS, NT = Cfg::NT;
+  using Cfg = RecCfg<MODE, H, C, BS, KL, UPL, RG>;
+  using LM = LaneMap<KL, UPL, BS>;
+  constexpr int G = Cfg::G, HS = Cfg::HS, NT = Cfg::NT, UPW = Cfg::UPW, NSM = Cfg::NSM, GH = Cfg::GH;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* W_s = reinterpret_cast<float*>(smem_raw);             // [G*HS][H]
-  float* h_s = W_s + (size_t)Cfg::NCOL * H;                    // [2][BS][H]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(h_s + 2 * BS * H);
+  float* W_s = reinterpret_cast<float*>(smem_raw);                 // [NSM*HS][H]
+  float* h_s = W_s + (size_t)NSM * HS * H;                         // [2][BS][H]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(h_s + 2 * BS * H);  // [0] weights, [1..2] state buffers
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -81,32 +103,35 @@ __global__ void __launch_bounds__(FwdCfg<MODE, H, C, BS, UPW>::NT, 1)
   const int b0 = slice * BS;
   const int j0 = (int)rank * HS;
   const int B = p.B, T = p.T;
+  const float* w_hh = p.w_hh[dir];
 
-  // ---- stage this CTA's rows of W_hh (G blocks of HS contiguous rows) with TMA bulk copies ----------
   if (tid == 0) {
-    ptx::mbar_init(bar, 1);
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::mbar_init(&bars[2], 1);
     ptx::fence_mbar_init();
   }
   __syncthreads();
   if (tid == 0) {
-    ptx::mbar_arrive_expect_tx(bar, (uint32_t)Cfg::W_BYTES);
-    const float* w_hh = p.w_hh[dir];
+    // this CTA's rows of the first NSM gate blocks of W_hh: NSM contiguous [HS,H] blocks, one TMA bulk copy each
+    ptx::mbar_arrive_expect_tx(&bars[0], (uint32_t)Cfg::W_BYTES);
 #pragma unroll
-    for (int g = 0; g < G; ++g)
+    for (int g = 0; g < NSM; ++g)
       ptx::tma_bulk_g2s(W_s + (size_t)g * HS * H, w_hh + ((size_t)g * H + j0) * H,
-                        (uint32_t)(HS * H * sizeof(float)), bar);
+                        (uint32_t)(HS * H * sizeof(float)), &bars[0]);
   }
   for (int i = tid; i < 2 * BS * H; i += NT) h_s[i] = 0.f;  // h_0 = 0 (rnn.py:1432-1440)
-  ptx::mbar_wait(bar, 0);
+  float wreg[1][UPL][H / KL];
+  load_resident<RG, KL, UPL, BS, H>(w_hh, H, (long long)NSM * H + j0 + w * UPW, lane, wreg);
+  ptx::mbar_wait(&bars[0], 0);
   __syncthreads();
-  ptx::cluster_sync_all();  // every CTA's state buffers are initialised before any peer writes into them
+  ptx::cluster_sync_all();  // peers' barriers and state buffers are initialised before anyone writes into them
 
   // ---- lane identity: after the butterfly this lane owns (unit, batch) ------------------------------
-  const int pu = LM::p(lane), qb = LM::q(lane), rep = LM::rep(lane);
-  const int j = j0 + w * UPW + pu;  // hidden unit
+  const int uw = LM::unit(lane), qb = LM::q(lane);
+  const int j = j0 + w * UPW + uw;  // hidden unit
   const int b = b0 + qb;            // batch row
   const bool valid = b < B;
-  const int GH = G * H;
   float* gates = p.gates[dir];
   float* extra = p.extra[dir];
   const float bhn = (MODE == B200RNN_GRU) ? p.b_hh[dir][2 * H + j] : 0.f;
@@ -124,12 +149,15 @@ __global__ void __launch_bounds__(FwdCfg<MODE, H, C, BS, UPW>::NT, 1)
 
   for (int step = 0; step < T; ++step) {
     const int t = dir ? (T - 1 - step) : step;
-    const float* h_cur = h_s + (step & 1) * BS * H;
-    float* h_nxt = h_s + ((step & 1) ^ 1) * BS * H;
+    const int cur = step & 1, nxt = cur ^ 1;
+    const float* h_cur = h_s + cur * BS * H;
+    float* h_nxt = h_s + nxt * BS * H;
+    if (step > 0) ptx::mbar_wait(&bars[1 + cur], ((step - 1) >> 1) & 1);  // h_step has fully arrived
+    if (tid == 0 && step + 1 < T) ptx::mbar_arrive_expect_tx(&bars[1 + nxt], (uint32_t)(BS * H * sizeof(float)));
 
-    float acc[G][UPW][BS];
-    warp_partial_dots<G, UPW, BS, H>(W_s, HS, w * UPW, h_cur, lane, acc);
-    warp_transpose_reduce<G, UPW, BS>(acc);
+    float acc[G][UPL][BS];
+    warp_partial_dots<G, RG, KL, UPL, BS, H>(W_s, HS, w * UPW, wreg, h_cur, lane, acc);
+    warp_transpose_reduce<G, KL, UPL, BS>(acc);
 
     float hnew, s0, s1, s2, s3 = 0.f, sx;
     if (MODE == B200RNN_GRU) {
@@ -151,16 +179,10 @@ __global__ void __launch_bounds__(FwdCfg<MODE, H, C, BS, UPW>::NT, 1)
     }
     h_prev = hnew;
 
-    // all-gather the new state into every CTA of the cluster (DSMEM), replicas split the peers
-    {
-      const uint32_t laddr = ptx::smem_u32(&h_nxt[qb * H + j]);
-      for (int rk = rep; rk < C; rk += LM::NREP) ptx::st_cluster_f32(ptx::mapa(laddr, (uint32_t)rk), hnew);
-    }
-    __syncwarp();
-    ptx::cluster_arrive_release();
+    if (step + 1 < T) allgather_units<C, KL, UPL, BS>(hnew, h_nxt, H, j0 + w * UPW, &bars[1 + nxt], lane);
 
     // off the critical path: global stores of this step, prefetch of the next step's x-projection
-    if (valid && rep == 0) {
+    if (valid) {
       p.y[(long long)t * p.y_st + (long long)b * p.y_sb + dir * H + j] = hnew;
       if (p.training) {
         float* gp = gates + ((size_t)t * B + b) * GH + j;
@@ -174,31 +196,52 @@ __global__ void __launch_bounds__(FwdCfg<MODE, H, C, BS, UPW>::NT, 1)
         p.h_n[((size_t)dir * B + b) * H + j] = hnew;
         if (MODE == B200RNN_LSTM && p.c_n) p.c_n[((size_t)dir * B + b) * H + j] = c_prev;
       }
-    }
-    if (valid && step + 1 < T) {
-      const int tn = dir ? (T - 2 - step) : (step + 1);
-      const float* gp = gates + ((size_t)tn * B + b) * GH + j;
+      if (step + 1 < T) {
+        const int tn = dir ? (T - 2 - step) : (step + 1);
+        const float* gp = gates + ((size_t)tn * B + b) * GH + j;
 #pragma unroll
-      for (int g = 0; g < G; ++g) gi[g] = gp[g * H];
+        for (int g = 0; g < G; ++g) gi[g] = gp[g * H];
+      }
     }
-    __syncwarp();
-    ptx::cluster_wait_acquire();
   }
+  ptx::cluster_sync_all();  // nobody exits while a peer could still address its shared memory
 }
 
 // =================================================================================================
 // backward (BPTT)
 // =================================================================================================
-template <int MODE, int H, int C, int BS, int UPW>
-__global__ void __launch_bounds__(BwdCfg<MODE, H, C, BS, UPW>::NT, 1)
+// w_prep layout (written by whh_prep_kernel): [C ranks][G][HS][H],
+//   w_prep[rank][g][u][jj] = W_hh[g*H + jj][rank*HS + u]
+// i.e. for every gate block the transposed slice a CTA needs, contiguous per CTA (TMA bulk copyable).
+__global__ void whh_prep_kernel(const float* __restrict__ w_hh, float* __restrict__ out, int G, int H, int C) {
+  __shared__ float tile[32][33];
+  const int HS = H / C;
+  const int tiles_per_g = (H / 32) * (H / 32);
+  for (int tix = blockIdx.x; tix < G * tiles_per_g; tix += gridDim.x) {
+    const int g = tix / tiles_per_g, rem = tix - g * tiles_per_g;
+    const int tj = rem / (H / 32), tk = rem - tj * (H / 32);  // tj: row tile of the gate block, tk: column tile
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+      tile[i][threadIdx.x] = w_hh[((size_t)g * H + tj * 32 + i) * H + tk * 32 + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int col = tk * 32 + i;  // column of W_hh = output unit of the backward contraction
+      const int rk = col / HS, u = col - rk * HS;
+      out[(((size_t)rk * G + g) * HS + u) * H + tj * 32 + threadIdx.x] = tile[threadIdx.x][i];
+    }
+    __syncthreads();
+  }
+}
+
+template <int MODE, int H, int C, int BS, int KL, int UPL, int RG>
+__global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     rec_bwd_kernel(const RecBwdParams p, const int nslices) {
-  using Cfg = BwdCfg<MODE, H, C, BS, UPW>;
-  using LM = LaneMap<UPW, BS>;
-  constexpr int G = Cfg::G, GH = Cfg::GH, HS = Cfg::HS, NT = Cfg::NT;
+  using Cfg = RecCfg<MODE, H, C, BS, KL, UPL, RG>;
+  using LM = LaneMap<KL, UPL, BS>;
+  constexpr int G = Cfg::G, GH = Cfg::GH, HS = Cfg::HS, NT = Cfg::NT, UPW = Cfg::UPW, NSM = Cfg::NSM;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* W_s = reinterpret_cast<float*>(smem_raw);   // [HS][G*H]  rows of W_hh^T = columns of W_hh
-  float* d_s = W_s + (size_t)HS * GH;                // [2][BS][G*H] gate gradients of the whole cluster
-  uint64_t* bar = reinterpret_cast<uint64_t*>(d_s + 2 * BS * GH);
+  float* W_s = reinterpret_cast<float*>(smem_raw);   // [NSM][HS][H] transposed gate blocks
+  float* d_s = W_s + (size_t)NSM * HS * H;           // [2][BS][G*H] gate gradients of the whole cluster
+  uint64_t* bars = reinterpret_cast<uint64_t*>(d_s + 2 * BS * GH);
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -208,29 +251,31 @@ __global__ void __launch_bounds__(BwdCfg<MODE, H, C, BS, UPW>::NT, 1)
   const int b0 = slice * BS;
   const int j0 = (int)rank * HS;
   const int B = p.B, T = p.T;
+  const float* w_prep = p.w_prep[dir] + (size_t)rank * G * HS * H;
 
   if (tid == 0) {
-    ptx::mbar_init(bar, 1);
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::mbar_init(&bars[2], 1);
     ptx::fence_mbar_init();
   }
   __syncthreads();
   if (tid == 0) {
-    ptx::mbar_arrive_expect_tx(bar, (uint32_t)Cfg::W_BYTES);
-    // HS consecutive rows of W_hh^T are one contiguous block; split so each copy stays well below 2^20 B
-    constexpr int NCHUNK = 4;
-    constexpr uint32_t CH = (uint32_t)(Cfg::W_BYTES / NCHUNK);
-    const char* src = reinterpret_cast<const char*>(p.w_hh_t[dir] + (size_t)j0 * GH);
+    ptx::mbar_arrive_expect_tx(&bars[0], (uint32_t)Cfg::W_BYTES);
 #pragma unroll
-    for (int c = 0; c < NCHUNK; ++c)
-      ptx::tma_bulk_g2s(reinterpret_cast<char*>(W_s) + (size_t)c * CH, src + (size_t)c * CH, CH, bar);
+    for (int g = 0; g < NSM; ++g)
+      ptx::tma_bulk_g2s(W_s + (size_t)g * HS * H, w_prep + (size_t)g * HS * H, (uint32_t)(HS * H * sizeof(float)),
+                        &bars[0]);
   }
   for (int i = tid; i < 2 * BS * GH; i += NT) d_s[i] = 0.f;
-  ptx::mbar_wait(bar, 0);
+  float wreg[1][UPL][H / KL];
+  load_resident<RG, KL, UPL, BS, H>(w_prep + (size_t)NSM * HS * H, HS, (long long)w * UPW, lane, wreg);
+  ptx::mbar_wait(&bars[0], 0);
   __syncthreads();
   ptx::cluster_sync_all();
 
-  const int pu = LM::p(lane), qb = LM::q(lane), rep = LM::rep(lane);
-  const int j = j0 + w * UPW + pu;
+  const int uw = LM::unit(lane), qb = LM::q(lane);
+  const int j = j0 + w * UPW + uw;
   const int b = b0 + qb;
   const bool valid = b < B;
   const float* gates = p.gates[dir];
@@ -268,8 +313,10 @@ __global__ void __launch_bounds__(BwdCfg<MODE, H, C, BS, UPW>::NT, 1)
 
   for (int step = 0; step < T; ++step) {
     const int t = dir ? step : (T - 1 - step);
-    float* d_nxt = d_s + (step & 1) * BS * GH;
+    const int buf = step & 1;
+    float* d_buf = d_s + buf * BS * GH;
     const bool last = (step == T - 1);
+    if (tid == 0 && !last) ptx::mbar_arrive_expect_tx(&bars[1 + buf], (uint32_t)(BS * GH * sizeof(float)));
 
     // ---- cell backward for (unit j, batch b) ----------------------------------------------------
     const float dh = dh_carry + dyv;
@@ -302,22 +349,16 @@ __global__ void __launch_bounds__(BwdCfg<MODE, H, C, BS, UPW>::NT, 1)
 
     if (!last) {
       // all-gather the recurrent-side gate gradient (GRU: n-gate part is dn*r) into every peer CTA
-      const uint32_t laddr = ptx::smem_u32(&d_nxt[qb * GH + j]);
-      for (int rk = rep; rk < C; rk += LM::NREP) {
-        const uint32_t ra = ptx::mapa(laddr, (uint32_t)rk);
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          float v = dg[g];
-          if (MODE == B200RNN_GRU && g == 2) v = dhn;
-          if (!valid) v = 0.f;
-          ptx::st_cluster_f32(ra + (uint32_t)(g * H * sizeof(float)), v);
-        }
+      for (int g = 0; g < G; ++g) {
+        float v = dg[g];
+        if (MODE == B200RNN_GRU && g == 2) v = dhn;
+        if (!valid) v = 0.f;
+        allgather_units<C, KL, UPL, BS>(v, d_buf, GH, g * H + j0 + w * UPW, &bars[1 + buf], lane);
       }
-      __syncwarp();
-      ptx::cluster_arrive_release();
     }
 
-    if (valid && rep == 0) {
+    if (valid) {
       float* gp = dgates + ((size_t)t * B + b) * GH + j;
 #pragma unroll
       for (int g = 0; g < G; ++g) gp[g * H] = dg[g];
@@ -325,31 +366,41 @@ __global__ void __launch_bounds__(BwdCfg<MODE, H, C, BS, UPW>::NT, 1)
     }
     if (last) break;
     if (valid) load_step(step + 1);
-    __syncwarp();
-    ptx::cluster_wait_acquire();
+    ptx::mbar_wait(&bars[1 + buf], (step >> 1) & 1);  // every CTA's slice of this step's gate gradient arrived
 
-    // ---- dh_{prev}[b][j] = direct + sum_col dgh[b][col] * W_hh[col][j] -----------------------------
-    float acc[1][UPW][BS];
-    warp_partial_dots<1, UPW, BS, GH>(W_s, 0, w * UPW, d_nxt, lane, acc);
-    warp_transpose_reduce<1, UPW, BS>(acc);
+    // ---- dh_{prev}[b][j] = direct + sum_col dgh[b][col] * W_hh[col][j], one gate block of columns at a time ----
+    float acc[1][UPL][BS];
+#pragma unroll
+    for (int au = 0; au < UPL; ++au)
+#pragma unroll
+      for (int ab = 0; ab < BS; ++ab) acc[0][au][ab] = 0.f;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (g < NSM)
+        warp_partial_dots<1, 0, KL, UPL, BS, H, GH, false>(W_s + (size_t)g * HS * H, 0, w * UPW, wreg,
+                                                            d_buf + g * H, lane, acc);
+      else
+        warp_partial_dots<1, 1, KL, UPL, BS, H, GH, false>(W_s, 0, 0, wreg, d_buf + g * H, lane, acc);
+    }
+    warp_transpose_reduce<1, KL, UPL, BS>(acc);
     dh_carry = direct + acc[0][0][0];
   }
 
-  // ---- per-slice bias-gradient partials: sum over this slice's batch rows (lane bits of q) ----------
-  constexpr unsigned FULL = 0xffffffffu;
+  // ---- per-slice bias-gradient partials: sum over this slice's batch rows (the low lane bits) -------------
 #pragma unroll
   for (int g = 0; g <= G; ++g) {
     float v = bsum[g];
 #pragma unroll
-    for (int off = LM::NREP; off < LM::NREP * BS; off <<= 1) v += __shfl_xor_sync(FULL, v, off);
+    for (int off = 1; off < BS; off <<= 1) v += __shfl_xor_sync(FULLMASK, v, off);
     bsum[g] = v;
   }
-  if (qb == 0 && rep == 0) {
+  if (qb == 0) {
     float* out = p.dbias_part[dir] + (size_t)slice * (G + 1) * H;
 #pragma unroll
     for (int g = 0; g < G; ++g) out[g * H + j] = bsum[g];
     out[G * H + j] = bsum[G];
   }
+  ptx::cluster_sync_all();
 }
 
 // =================================================================================================
@@ -358,13 +409,13 @@ __global__ void __launch_bounds__(BwdCfg<MODE, H, C, BS, UPW>::NT, 1)
 template <typename K>
 int prepare_kernel(K kernel, size_t smem) {
   static std::mutex mu;  // forward and autograd-backward threads both launch
-  static const void* done[64];
+  static const void* done[128];
   static int ndone = 0;
   std::lock_guard<std::mutex> lk(mu);
   for (int i = 0; i < ndone; ++i)
     if (done[i] == (const void*)kernel) return B200RNN_OK;
   B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (ndone < 64) done[ndone++] = (const void*)kernel;
+  if (ndone < 128) done[ndone++] = (const void*)kernel;
   return B200RNN_OK;
 }
 
@@ -399,11 +450,13 @@ int max_active_clusters(K kernel, int C, int NT, size_t smem) {
     int n;
   };
   static std::mutex mu;
-  static Entry cache[64];
+  static Entry cache[128];
   static int ncache = 0;
-  std::lock_guard<std::mutex> lk(mu);
-  for (int i = 0; i < ncache; ++i)
-    if (cache[i].k == (const void*)kernel) return cache[i].n;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    for (int i = 0; i < ncache; ++i)
+      if (cache[i].k == (const void*)kernel) return cache[i].n;
+  }
   if (prepare_kernel(kernel, smem) != B200RNN_OK) return 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(C * 148), 1, 1);
@@ -421,65 +474,90 @@ int max_active_clusters(K kernel, int C, int NT, size_t smem) {
     cudaGetLastError();
     n = 0;
   }
-  if (ncache < 64) cache[ncache++] = Entry{(const void*)kernel, n};
+  std::lock_guard<std::mutex> lk(mu);
+  if (ncache < 128) cache[ncache++] = Entry{(const void*)kernel, n};
   return n;
 }
 
-template <int MODE, int H, int C, int BS, int UPW>
+template <int MODE, int H, int C, int BS, int KL, int UPL, int RG>
 bool try_fwd(const RecFwdParams& p, cudaStream_t s, bool force, int* rc) {
-  using Cfg = FwdCfg<MODE, H, C, BS, UPW>;
-  auto k = rec_fwd_kernel<MODE, H, C, BS, UPW>;
+  using Cfg = RecCfg<MODE, H, C, BS, KL, UPL, RG>;
+  static_assert(Cfg::FWD_SMEM <= MAX_SMEM, "forward config does not fit an SM");
+  auto k = rec_fwd_kernel<MODE, H, C, BS, KL, UPL, RG>;
   const int nslices = (p.B + BS - 1) / BS;
   const int nclusters = nslices * p.D;
-  if (!force && nclusters > max_active_clusters(k, C, Cfg::NT, Cfg::SMEM)) return false;
-  *rc = launch_clustered(k, p, nslices, nclusters, C, Cfg::NT, Cfg::SMEM, s, PROF_REC_FWD);
+  if (!force && nclusters > max_active_clusters(k, C, Cfg::NT, Cfg::FWD_SMEM)) return false;
+  *rc = launch_clustered(k, p, nslices, nclusters, C, Cfg::NT, Cfg::FWD_SMEM, s, PROF_REC_FWD);
   return true;
 }
 
-template <int MODE, int H, int C, int BS, int UPW>
+template <int MODE, int H, int C, int BS, int KL, int UPL, int RG>
 bool try_bwd(RecBwdParams& p, cudaStream_t s, bool force, int* rc) {
-  using Cfg = BwdCfg<MODE, H, C, BS, UPW>;
-  auto k = rec_bwd_kernel<MODE, H, C, BS, UPW>;
+  using Cfg = RecCfg<MODE, H, C, BS, KL, UPL, RG>;
+  static_assert(Cfg::BWD_SMEM <= MAX_SMEM, "backward config does not fit an SM");
+  auto k = rec_bwd_kernel<MODE, H, C, BS, KL, UPL, RG>;
   const int nslices = (p.B + BS - 1) / BS;
   const int nclusters = nslices * p.D;
-  if (!force && nclusters > max_active_clusters(k, C, Cfg::NT, Cfg::SMEM)) return false;
+  if (!force && nclusters > max_active_clusters(k, C, Cfg::NT, Cfg::BWD_SMEM)) return false;
+  // transposed, per-CTA contiguous copy of W_hh for this cluster width
+  for (int d = 0; d < p.D; ++d) {
+    whh_prep_kernel<<<148, dim3(32, 8), 0, s>>>(p.w_hh[d], p.w_prep[d], Cfg::G, H, C);
+    if (cudaGetLastError() != cudaSuccess) {
+      set_error("whh_prep launch failed");
+      *rc = B200RNN_ERR_CUDA;
+      return true;
+    }
+    count_launch();
+  }
   p.nslices_out = nslices;
-  *rc = launch_clustered(k, p, nslices, nclusters, C, Cfg::NT, Cfg::SMEM, s, PROF_REC_BWD);
+  *rc = launch_clustered(k, p, nslices, nclusters, C, Cfg::NT, Cfg::BWD_SMEM, s, PROF_REC_BWD);
   return true;
+}
+
+int env_variant(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
 }
 
 }  // namespace
 
-// smallest BS any backward config uses is 2
-int rec_bwd_max_slices(int B) { return (B + 1) / 2; }
+// smallest BS any backward config uses is 4
+int rec_bwd_max_slices(int B) { return (B + 3) / 4; }
 
 // Candidates are ordered by batch rows per cluster; the first one whose clusters are all co-resident
 // (one wave => every sequence advances in lock step) wins, else the widest one runs in several waves.
+// Template arguments: <MODE, H, C, BS, KL, UPL, RG>.
 int launch_rec_fwd(const RecFwdParams& p, cudaStream_t s) {
   int rc = B200RNN_OK;
   if (p.B <= 0 || p.T <= 0) return rc;
+  static const int variant = env_variant("B200RNN_FWD_VARIANT");  // tuning knob for the GRU H=256 forward
   if (p.mode == B200RNN_GRU && p.H == 256) {
-    if (try_fwd<B200RNN_GRU, 256, 4, 2, 4>(p, s, false, &rc)) return rc;
-    if (try_fwd<B200RNN_GRU, 256, 4, 4, 4>(p, s, false, &rc)) return rc;
-    try_fwd<B200RNN_GRU, 256, 8, 8, 2>(p, s, true, &rc);
+    if (variant == 1) {
+      if (try_fwd<B200RNN_GRU, 256, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    } else if (variant == 2) {
+      if (try_fwd<B200RNN_GRU, 256, 4, 4, 8, 2, 0>(p, s, false, &rc)) return rc;
+    } else if (variant == 3) {
+      try_fwd<B200RNN_GRU, 256, 8, 8, 32, 4, 1>(p, s, true, &rc);
+      return rc;
+    } else {
+      if (try_fwd<B200RNN_GRU, 256, 4, 4, 32, 8, 1>(p, s, false, &rc)) return rc;
+    }
+    try_fwd<B200RNN_GRU, 256, 8, 8, 32, 4, 1>(p, s, true, &rc);
     return rc;
   }
   if (p.mode == B200RNN_GRU && p.H == 128) {
-    if (try_fwd<B200RNN_GRU, 128, 2, 2, 4>(p, s, false, &rc)) return rc;
-    if (try_fwd<B200RNN_GRU, 128, 2, 4, 4>(p, s, false, &rc)) return rc;
-    try_fwd<B200RNN_GRU, 128, 4, 8, 2>(p, s, true, &rc);
+    if (try_fwd<B200RNN_GRU, 128, 2, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    try_fwd<B200RNN_GRU, 128, 4, 8, 32, 4, 1>(p, s, true, &rc);
     return rc;
   }
   if (p.mode == B200RNN_LSTM && p.H == 256) {
-    if (try_fwd<B200RNN_LSTM, 256, 8, 2, 4>(p, s, false, &rc)) return rc;
-    if (try_fwd<B200RNN_LSTM, 256, 8, 4, 4>(p, s, false, &rc)) return rc;
-    try_fwd<B200RNN_LSTM, 256, 8, 8, 2>(p, s, true, &rc);
+    if (try_fwd<B200RNN_LSTM, 256, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    try_fwd<B200RNN_LSTM, 256, 8, 8, 16, 2, 1>(p, s, true, &rc);
     return rc;
   }
   if (p.mode == B200RNN_LSTM && p.H == 128) {
-    if (try_fwd<B200RNN_LSTM, 128, 2, 2, 4>(p, s, false, &rc)) return rc;
-    if (try_fwd<B200RNN_LSTM, 128, 2, 4, 4>(p, s, false, &rc)) return rc;
-    try_fwd<B200RNN_LSTM, 128, 4, 8, 2>(p, s, true, &rc);
+    if (try_fwd<B200RNN_LSTM, 128, 2, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    try_fwd<B200RNN_LSTM, 128, 4, 8, 16, 2, 1>(p, s, true, &rc);
     return rc;
   }
   set_error("recurrence: unsupported (mode=%d, hidden_size=%d); built for hidden_size 128 and 256", p.mode,
@@ -491,27 +569,23 @@ int launch_rec_bwd(RecBwdParams& p, cudaStream_t s) {
   int rc = B200RNN_OK;
   if (p.B <= 0 || p.T <= 0) return rc;
   if (p.mode == B200RNN_GRU && p.H == 256) {
-    if (try_bwd<B200RNN_GRU, 256, 4, 2, 8>(p, s, false, &rc)) return rc;
-    if (try_bwd<B200RNN_GRU, 256, 4, 4, 8>(p, s, false, &rc)) return rc;
-    try_bwd<B200RNN_GRU, 256, 8, 8, 4>(p, s, true, &rc);
+    if (try_bwd<B200RNN_GRU, 256, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    try_bwd<B200RNN_GRU, 256, 8, 8, 32, 4, 1>(p, s, true, &rc);
     return rc;
   }
   if (p.mode == B200RNN_GRU && p.H == 128) {
-    if (try_bwd<B200RNN_GRU, 128, 2, 2, 8>(p, s, false, &rc)) return rc;
-    if (try_bwd<B200RNN_GRU, 128, 2, 4, 8>(p, s, false, &rc)) return rc;
-    try_bwd<B200RNN_GRU, 128, 4, 8, 4>(p, s, true, &rc);
+    if (try_bwd<B200RNN_GRU, 128, 2, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    try_bwd<B200RNN_GRU, 128, 4, 8, 32, 4, 1>(p, s, true, &rc);
     return rc;
   }
   if (p.mode == B200RNN_LSTM && p.H == 256) {
-    if (try_bwd<B200RNN_LSTM, 256, 8, 2, 4>(p, s, false, &rc)) return rc;
-    if (try_bwd<B200RNN_LSTM, 256, 8, 4, 4>(p, s, false, &rc)) return rc;
-    try_bwd<B200RNN_LSTM, 256, 8, 8, 4>(p, s, true, &rc);
+    if (try_bwd<B200RNN_LSTM, 256, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    try_bwd<B200RNN_LSTM, 256, 8, 8, 32, 4, 1>(p, s, true, &rc);
     return rc;
   }
   if (p.mode == B200RNN_LSTM && p.H == 128) {
-    if (try_bwd<B200RNN_LSTM, 128, 2, 2, 8>(p, s, false, &rc)) return rc;
-    if (try_bwd<B200RNN_LSTM, 128, 2, 4, 8>(p, s, false, &rc)) return rc;
-    try_bwd<B200RNN_LSTM, 128, 4, 8, 4>(p, s, true, &rc);
+    if (try_bwd<B200RNN_LSTM, 128, 2, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    try_bwd<B200RNN_LSTM, 128, 4, 8, 32, 4, 1>(p, s, true, &rc);
     return rc;
   }
   set_error("recurrence backward: unsupported (mode=%d, hidden_size=%d)", p.mode, p.H);

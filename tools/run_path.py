@@ -18,6 +18,7 @@ ap.add_argument("what")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--B", type=int, default=128)
 ap.add_argument("--T", type=int, default=0)
+ap.add_argument("--time", action="store_true")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -48,4 +49,26 @@ else:
         y = m(x)[0]
         y.sum().backward()
 torch.cuda.synchronize()
+if args.time:
+    from b200rnn import _lib
+    _lib.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    e0.record()
+    if args.what.endswith("fwd"):
+        with torch.no_grad():
+            for _ in range(n):
+                m(x)
+    elif args.what != "gemm":
+        for _ in range(n):
+            m.zero_grad()
+            m(x)[0].sum().backward()
+    e1.record()
+    torch.cuda.synchronize()
+    out = {"what": args.what, "B": args.B, "ms_per_iter": e0.elapsed_time(e1) / n}
+    for name, kind in (("rec_fwd", 0), ("rec_bwd", 1), ("gemm", 2)):
+        ms, cnt = _lib.profile_read(kind)
+        out[name] = f"{ms / max(cnt, 1) * 1e3:.1f} us x{cnt // n}/iter"
+    _lib.profile(False)
+    print(out)
 print("done", args.what)

@@ -50,81 +50,75 @@ struct LaneMap {
   }
 };
 
-// Load the register-resident row-groups: wreg[r][au][e] for k = chunk*4*KL + kl*4 + (e&3).
-//   Wg : global weight matrix, row-major with leading dimension KLEN; row of (group r, unit u) = grow0 + r*gstride + u
+// The contraction dimension is processed in chunks of CW = 4*KL floats. `rot` rotates the chunk order per CTA
+// (chunk c of the loop works on actual chunk ca = (c + rot) % NCH) so that a CTA starts with the slice of the
+// state vector it produced itself while its peers' slices are still in flight; register-resident weights are
+// loaded in that rotated order, so their register indices stay compile-time constants.
+
+// Load the register-resident row-groups: wreg[r][au][c*4 + e] = W[row][ca*CW + kl*4 + e].
+//   Wg : global weight matrix, row-major, leading dimension KLEN; row of (group r, unit u) = grow0 + r*gstride + u
 template <int RG, int KL, int UPL, int BS, int KLEN>
 __device__ __forceinline__ void load_resident(const float* __restrict__ Wg, long long gstride_rows, long long grow0,
-                                              int lane, float (&wreg)[RG > 0 ? RG : 1][UPL][KLEN / KL]) {
+                                              int rot, int lane, float (&wreg)[RG > 0 ? RG : 1][UPL][KLEN / KL]) {
   using LM = LaneMap<KL, UPL, BS>;
-  const int kl = LM::kl(lane), p = LM::p(lane), c = LM::cl(lane);
+  constexpr int NCH = KLEN / (4 * KL);
+  const int kl = LM::kl(lane), p = LM::p(lane), cgrp = LM::cl(lane);
 #pragma unroll
   for (int r = 0; r < RG; ++r)
 #pragma unroll
     for (int au = 0; au < UPL; ++au) {
-      const float* row = Wg + (grow0 + (long long)r * gstride_rows + c * UPL + (au ^ p)) * KLEN;
+      const float* row = Wg + (grow0 + (long long)r * gstride_rows + cgrp * UPL + (au ^ p)) * KLEN;
 #pragma unroll
-      for (int i = 0; i < KLEN / (4 * KL); ++i) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(row + i * 4 * KL + kl * 4));
-        wreg[r][au][i * 4 + 0] = v.x;
-        wreg[r][au][i * 4 + 1] = v.y;
-        wreg[r][au][i * 4 + 2] = v.z;
-        wreg[r][au][i * 4 + 3] = v.w;
+      for (int c = 0; c < NCH; ++c) {
+        const int ca = (c + rot) % NCH;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row + ca * 4 * KL + kl * 4));
+        wreg[r][au][c * 4 + 0] = v.x;
+        wreg[r][au][c * 4 + 1] = v.y;
+        wreg[r][au][c * 4 + 2] = v.z;
+        wreg[r][au][c * 4 + 3] = v.w;
       }
     }
 }
 
-// acc[r][au][ab] = sum over this lane's k of  W[row(r, au^p)][k] * vec[ab^q][k]      (partial sums)
-//   W_s   : shared-memory weight slice holding the first NR-RG row-groups, row-major [.][KLEN];
+// One chunk of the contraction:
+//   acc[r][au][ab] += sum_{k in chunk ca, this lane} W[row(r, au^p)][k] * vec[ab^q][k]
+//   W_s   : shared-memory weights of the first NR-RG row-groups, row-major [.][KLEN];
 //           row of (group r, unit u of this warp) = r*group_stride + row0 + u
-//   wreg  : the last RG row-groups, register resident (see load_resident)
-//   vec_s : [BS][KLEN]
-//   VSTRIDE : floats between consecutive batch rows of vec_s;  ZERO : start from 0 (else accumulate)
-template <int NR, int RG, int KL, int UPL, int BS, int KLEN, int VSTRIDE = KLEN, bool ZERO = true>
-__device__ __forceinline__ void warp_partial_dots(const float* __restrict__ W_s, int group_stride, int row0,
-                                                  const float (&wreg)[RG > 0 ? RG : 1][UPL][KLEN / KL],
-                                                  const float* __restrict__ vec_s, int lane,
-                                                  float (&acc)[NR][UPL][BS]) {
+//   wreg  : the last RG row-groups, register resident (see load_resident), indexed by the LOOP chunk index c
+//   vec_s : BS vectors, VSTRIDE floats apart
+template <int NR, int RG, int KL, int UPL, int BS, int KLEN, int VSTRIDE>
+__device__ __forceinline__ void dots_chunk(const float* __restrict__ W_s, int group_stride, int row0,
+                                           const float (&wreg)[RG > 0 ? RG : 1][UPL][KLEN / KL],
+                                           const float* __restrict__ vec_s, int c, int ca, int lane,
+                                           float (&acc)[NR][UPL][BS]) {
   using LM = LaneMap<KL, UPL, BS>;
   static_assert(KLEN % (4 * KL) == 0, "contraction length must be a multiple of 4*KL");
-  const int kl = LM::kl(lane), p = LM::p(lane), q = LM::q(lane), c = LM::cl(lane);
-  if (ZERO) {
+  const int kl = LM::kl(lane), p = LM::p(lane), q = LM::q(lane), cgrp = LM::cl(lane);
+  const int koff = ca * 4 * KL + kl * 4;
+  float4 hv[BS];
 #pragma unroll
-    for (int r = 0; r < NR; ++r)
+  for (int ab = 0; ab < BS; ++ab) hv[ab] = *reinterpret_cast<const float4*>(&vec_s[(ab ^ q) * VSTRIDE + koff]);
 #pragma unroll
-      for (int au = 0; au < UPL; ++au)
+  for (int r = 0; r < NR; ++r) {
 #pragma unroll
-        for (int ab = 0; ab < BS; ++ab) acc[r][au][ab] = 0.f;
-  }
-
+    for (int au = 0; au < UPL; ++au) {
+      float4 wv;
+      if (r < NR - RG) {
+        const int row = r * group_stride + row0 + cgrp * UPL + (au ^ p);
+        wv = *reinterpret_cast<const float4*>(&W_s[row * KLEN + koff]);
+      } else {
+        const int ri = (r - (NR - RG)) > 0 ? (r - (NR - RG)) : 0;
+        wv = make_float4(wreg[ri][au][c * 4 + 0], wreg[ri][au][c * 4 + 1], wreg[ri][au][c * 4 + 2],
+                         wreg[ri][au][c * 4 + 3]);
+      }
 #pragma unroll
-  for (int i = 0; i < KLEN / (4 * KL); ++i) {
-    const int koff = i * 4 * KL + kl * 4;
-    float4 hv[BS];
-#pragma unroll
-    for (int ab = 0; ab < BS; ++ab)
-      hv[ab] = *reinterpret_cast<const float4*>(&vec_s[(ab ^ q) * VSTRIDE + koff]);
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-#pragma unroll
-      for (int au = 0; au < UPL; ++au) {
-        float4 wv;
-        if (r < NR - RG) {
-          const int row = r * group_stride + row0 + c * UPL + (au ^ p);
-          wv = *reinterpret_cast<const float4*>(&W_s[row * KLEN + koff]);
-        } else {
-          const int ri = (r - (NR - RG)) > 0 ? (r - (NR - RG)) : 0;
-          wv = make_float4(wreg[ri][au][i * 4 + 0], wreg[ri][au][i * 4 + 1], wreg[ri][au][i * 4 + 2],
-                           wreg[ri][au][i * 4 + 3]);
-        }
-#pragma unroll
-        for (int ab = 0; ab < BS; ++ab) {
-          float a = acc[r][au][ab];
-          a = fmaf(wv.x, hv[ab].x, a);
-          a = fmaf(wv.y, hv[ab].y, a);
-          a = fmaf(wv.z, hv[ab].z, a);
-          a = fmaf(wv.w, hv[ab].w, a);
-          acc[r][au][ab] = a;
-        }
+      for (int ab = 0; ab < BS; ++ab) {
+        float a = acc[r][au][ab];
+        a = fmaf(wv.x, hv[ab].x, a);
+        a = fmaf(wv.y, hv[ab].y, a);
+        a = fmaf(wv.z, hv[ab].z, a);
+        a = fmaf(wv.w, hv[ab].w, a);
+        acc[r][au][ab] = a;
       }
     }
   }

@@ -43,9 +43,18 @@ struct RecCfg {
   static constexpr int NW = HS / UPW;
   static constexpr int NT = NW * 32;
   static constexpr int NSM = G - RG;  // gate blocks held in shared memory
+  static constexpr int CW = 4 * KL;   // floats of the contraction dimension per chunk
+  static constexpr int NCH = H / CW;  // chunks per state vector (per gate block in the backward)
+  static constexpr bool ROT = (CW <= HS);           // chunk order rotates so the CTA's own slice comes first
+  static constexpr int CPS = ROT ? HS / CW : 1;     // chunks per source slice (ROT)
+  static constexpr int SPC = ROT ? 1 : CW / HS;     // source slices per chunk (!ROT)
+  static constexpr int NBAR = 1 + 2 * C;            // [0] weights, [1 + buf*C + src] state slices
+  static constexpr size_t BAR_BYTES = 256;
   static constexpr size_t W_BYTES = (size_t)NSM * HS * H * sizeof(float);
-  static constexpr size_t FWD_SMEM = W_BYTES + (size_t)2 * BS * H * sizeof(float) + 32;
-  static constexpr size_t BWD_SMEM = W_BYTES + (size_t)2 * BS * GH * sizeof(float) + 32;
+  static constexpr size_t FWD_SMEM = W_BYTES + (size_t)2 * BS * H * sizeof(float) + BAR_BYTES;
+  static constexpr size_t BWD_SMEM = W_BYTES + (size_t)2 * BS * GH * sizeof(float) + BAR_BYTES;
+  static_assert(NBAR * 8 <= (int)BAR_BYTES, "barrier block too small");
+  static_assert(ROT ? (HS % CW == 0) : (CW % HS == 0), "chunks must tile the per-CTA slices");
   static_assert(RG == 0 || RG == 1, "at most one register-resident gate block");
   static_assert(HS * C == H && NW * UPW == HS && NW >= 1, "bad split");
   static_assert(UPW % 4 == 0, "the exchange packs 4 units per 16-byte store");
@@ -93,7 +102,8 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* W_s = reinterpret_cast<float*>(smem_raw);                 // [NSM*HS][H]
   float* h_s = W_s + (size_t)NSM * HS * H;                         // [2][BS][H]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(h_s + 2 * BS * H);  // [0] weights, [1..2] state buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(h_s + 2 * BS * H);  // [0] weights, [1 + buf*C + src] state slices
+  constexpr int NCH = Cfg::NCH, CPS = Cfg::CPS, SPC = Cfg::SPC;
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -106,9 +116,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
   const float* w_hh = p.w_hh[dir];
 
   if (tid == 0) {
-    ptx::mbar_init(&bars[0], 1);
-    ptx::mbar_init(&bars[1], 1);
-    ptx::mbar_init(&bars[2], 1);
+    for (int i = 0; i < Cfg::NBAR; ++i) ptx::mbar_init(&bars[i], 1);
     ptx::fence_mbar_init();
   }
   __syncthreads();
@@ -121,8 +129,9 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
                         (uint32_t)(HS * H * sizeof(float)), &bars[0]);
   }
   for (int i = tid; i < 2 * BS * H; i += NT) h_s[i] = 0.f;  // h_0 = 0 (rnn.py:1432-1440)
+  const int rot = Cfg::ROT ? (int)rank * CPS : 0;
   float wreg[1][UPL][H / KL];
-  load_resident<RG, KL, UPL, BS, H>(w_hh, H, (long long)NSM * H + j0 + w * UPW, lane, wreg);
+  load_resident<RG, KL, UPL, BS, H>(w_hh, H, (long long)NSM * H + j0 + w * UPW, rot, lane, wreg);
   ptx::mbar_wait(&bars[0], 0);
   __syncthreads();
   ptx::cluster_sync_all();  // peers' barriers and state buffers are initialised before anyone writes into them
@@ -152,11 +161,36 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     const int cur = step & 1, nxt = cur ^ 1;
     const float* h_cur = h_s + cur * BS * H;
     float* h_nxt = h_s + nxt * BS * H;
-    if (step > 0) ptx::mbar_wait(&bars[1 + cur], ((step - 1) >> 1) & 1);  // h_step has fully arrived
-    if (tid == 0 && step + 1 < T) ptx::mbar_arrive_expect_tx(&bars[1 + nxt], (uint32_t)(BS * H * sizeof(float)));
+    const uint32_t par = ((step - 1) >> 1) & 1;
 
     float acc[G][UPL][BS];
-    warp_partial_dots<G, RG, KL, UPL, BS, H>(W_s, HS, w * UPW, wreg, h_cur, lane, acc);
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int au = 0; au < UPL; ++au)
+#pragma unroll
+        for (int ab = 0; ab < BS; ++ab) acc[g][au][ab] = 0.f;
+    // contraction over h, one chunk at a time, starting with the slice this CTA produced itself; a chunk is
+    // touched only after the slice(s) it belongs to have arrived (per-source mbarriers)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ca = (c + rot) % NCH;
+      if (step > 0) {
+        if (Cfg::ROT) {
+          if (c % CPS == 0) ptx::mbar_wait(&bars[1 + cur * C + ca / CPS], par);
+        } else {
+#pragma unroll
+          for (int s2 = 0; s2 < SPC; ++s2) ptx::mbar_wait(&bars[1 + cur * C + ca * SPC + s2], par);
+        }
+      }
+      dots_chunk<G, RG, KL, UPL, BS, H, H>(W_s, HS, w * UPW, wreg, h_cur, c, ca, lane, acc);
+    }
+    // every slice of h_step has been consumed by this thread => the barriers of the other buffer are re-armed
+    if (tid == 0 && step + 1 < T) {
+#pragma unroll
+      for (int src = 0; src < C; ++src)
+        ptx::mbar_arrive_expect_tx(&bars[1 + nxt * C + src], (uint32_t)(BS * HS * sizeof(float)));
+    }
     warp_transpose_reduce<G, KL, UPL, BS>(acc);
 
     float hnew, s0, s1, s2, s3 = 0.f, sx;
@@ -164,22 +198,23 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
       const float r = sigmoid_f(gi[0] + acc[0][0][0]);
       const float z = sigmoid_f(gi[1] + acc[1][0][0]);
       const float hn = acc[2][0][0] + bhn;
-      const float n = tanhf(gi[2] + r * hn);
+      const float n = tanh_f(gi[2] + r * hn);
       hnew = n + z * (h_prev - n);
       s0 = r; s1 = z; s2 = n; sx = hn;
     } else {
       const float ig = sigmoid_f(gi[0] + acc[0][0][0]);
       const float fg = sigmoid_f(gi[1] + acc[1][0][0]);
-      const float gg = tanhf(gi[2] + acc[2][0][0]);
+      const float gg = tanh_f(gi[2] + acc[2][0][0]);
       const float og = sigmoid_f(gi[G - 1] + acc[G - 1][0][0]);
       const float cnew = fg * c_prev + ig * gg;
-      hnew = og * tanhf(cnew);
+      hnew = og * tanh_f(cnew);
       c_prev = cnew;
       s0 = ig; s1 = fg; s2 = gg; s3 = og; sx = cnew;
     }
     h_prev = hnew;
 
-    if (step + 1 < T) allgather_units<C, KL, UPL, BS>(hnew, h_nxt, H, j0 + w * UPW, &bars[1 + nxt], lane);
+    if (step + 1 < T)
+      allgather_units<C, KL, UPL, BS>(hnew, h_nxt, H, j0 + w * UPW, &bars[1 + nxt * C + rank], lane);
 
     // off the critical path: global stores of this step, prefetch of the next step's x-projection
     if (valid) {
@@ -241,7 +276,8 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* W_s = reinterpret_cast<float*>(smem_raw);   // [NSM][HS][H] transposed gate blocks
   float* d_s = W_s + (size_t)NSM * HS * H;           // [2][BS][G*H] gate gradients of the whole cluster
-  uint64_t* bars = reinterpret_cast<uint64_t*>(d_s + 2 * BS * GH);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(d_s + 2 * BS * GH);  // [0] weights, [1 + buf*C + src]
+  constexpr int NCH = Cfg::NCH, CPS = Cfg::CPS, SPC = Cfg::SPC;
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -254,9 +290,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
   const float* w_prep = p.w_prep[dir] + (size_t)rank * G * HS * H;
 
   if (tid == 0) {
-    ptx::mbar_init(&bars[0], 1);
-    ptx::mbar_init(&bars[1], 1);
-    ptx::mbar_init(&bars[2], 1);
+    for (int i = 0; i < Cfg::NBAR; ++i) ptx::mbar_init(&bars[i], 1);
     ptx::fence_mbar_init();
   }
   __syncthreads();
@@ -268,8 +302,9 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
                         &bars[0]);
   }
   for (int i = tid; i < 2 * BS * GH; i += NT) d_s[i] = 0.f;
+  const int rot = Cfg::ROT ? (int)rank * CPS : 0;
   float wreg[1][UPL][H / KL];
-  load_resident<RG, KL, UPL, BS, H>(w_prep + (size_t)NSM * HS * H, HS, (long long)w * UPW, lane, wreg);
+  load_resident<RG, KL, UPL, BS, H>(w_prep + (size_t)NSM * HS * H, HS, (long long)w * UPW, rot, lane, wreg);
   ptx::mbar_wait(&bars[0], 0);
   __syncthreads();
   ptx::cluster_sync_all();
@@ -316,7 +351,11 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     const int buf = step & 1;
     float* d_buf = d_s + buf * BS * GH;
     const bool last = (step == T - 1);
-    if (tid == 0 && !last) ptx::mbar_arrive_expect_tx(&bars[1 + buf], (uint32_t)(BS * GH * sizeof(float)));
+    if (tid == 0 && !last) {
+#pragma unroll
+      for (int src = 0; src < C; ++src)
+        ptx::mbar_arrive_expect_tx(&bars[1 + buf * C + src], (uint32_t)(BS * G * HS * sizeof(float)));
+    }
 
     // ---- cell backward for (unit j, batch b) ----------------------------------------------------
     const float dh = dh_carry + dyv;
@@ -331,7 +370,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
       direct = dh * z;
     } else {
       const float ig = sv[0], fg = sv[1], gg = sv[2], og = sv[G - 1];
-      const float tc = tanhf(sx);
+      const float tc = tanh_f(sx);
       const float dout = dh * tc * og * (1.f - og);
       const float dc = dc_carry + dh * og * (1.f - tc * tc);
       dg[0] = dc * gg * ig * (1.f - ig);
@@ -354,7 +393,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
         float v = dg[g];
         if (MODE == B200RNN_GRU && g == 2) v = dhn;
         if (!valid) v = 0.f;
-        allgather_units<C, KL, UPL, BS>(v, d_buf, GH, g * H + j0 + w * UPW, &bars[1 + buf], lane);
+        allgather_units<C, KL, UPL, BS>(v, d_buf, GH, g * H + j0 + w * UPW, &bars[1 + buf * C + rank], lane);
       }
     }
 
@@ -366,7 +405,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     }
     if (last) break;
     if (valid) load_step(step + 1);
-    ptx::mbar_wait(&bars[1 + buf], (step >> 1) & 1);  // every CTA's slice of this step's gate gradient arrived
+    const uint32_t par = (step >> 1) & 1;
 
     // ---- dh_{prev}[b][j] = direct + sum_col dgh[b][col] * W_hh[col][j], one gate block of columns at a time ----
     float acc[1][UPL][BS];
@@ -374,13 +413,24 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     for (int au = 0; au < UPL; ++au)
 #pragma unroll
       for (int ab = 0; ab < BS; ++ab) acc[0][au][ab] = 0.f;
+    // chunk by chunk over the source CTAs (own slice first); a source's G gate-gradient slices share one barrier
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      if (g < NSM)
-        warp_partial_dots<1, 0, KL, UPL, BS, H, GH, false>(W_s + (size_t)g * HS * H, 0, w * UPW, wreg,
-                                                            d_buf + g * H, lane, acc);
-      else
-        warp_partial_dots<1, 1, KL, UPL, BS, H, GH, false>(W_s, 0, 0, wreg, d_buf + g * H, lane, acc);
+    for (int c = 0; c < NCH; ++c) {
+      const int ca = (c + rot) % NCH;
+      if (Cfg::ROT) {
+        if (c % CPS == 0) ptx::mbar_wait(&bars[1 + buf * C + ca / CPS], par);
+      } else {
+#pragma unroll
+        for (int s2 = 0; s2 < SPC; ++s2) ptx::mbar_wait(&bars[1 + buf * C + ca * SPC + s2], par);
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (g < NSM)
+          dots_chunk<1, 0, KL, UPL, BS, H, GH>(W_s + (size_t)g * HS * H, 0, w * UPW, wreg, d_buf + g * H, c, ca,
+                                               lane, acc);
+        else
+          dots_chunk<1, 1, KL, UPL, BS, H, GH>(W_s, 0, 0, wreg, d_buf + g * H, c, ca, lane, acc);
+      }
     }
     warp_transpose_reduce<1, KL, UPL, BS>(acc);
     dh_carry = direct + acc[0][0][0];

@@ -72,7 +72,7 @@ class _RNNFunction(torch.autograd.Function):
         desc = _make_desc(cfg, B, T, save)
         rbytes, sbytes = _lib.workspace_bytes(desc)
         reserve = torch.empty(rbytes if save else 0, dtype=torch.uint8, device=dev)
-        scratch = torch.empty(0 if save else sbytes, dtype=torch.uint8, device=dev)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
         if cfg.batch_first:
             y = torch.empty(B, T, D * H, dtype=torch.float32, device=dev)
             ys_t, ys_b = D * H, T * D * H
@@ -86,7 +86,7 @@ class _RNNFunction(torch.autograd.Function):
             rc = lib.b200rnn_forward(
                 ctypes.byref(desc), x_tm.data_ptr(), x_tm.stride(0), x_tm.stride(1), params,
                 y.data_ptr(), ys_t, ys_b, h_n.data_ptr(), c_n.data_ptr() if c_n is not None else None,
-                reserve.data_ptr() if save else None, scratch.data_ptr() if not save else None,
+                reserve.data_ptr() if save else None, scratch.data_ptr(),
                 0, 0, rng_state.data_ptr() if rng_state is not None else None, _stream_ptr())
             _lib.check(rc, "b200rnn_forward")
         else:
@@ -216,7 +216,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kcontig: bool = True, b_kcontig:
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
         assert not accumulate
-    sbytes = M * N * 4 * 64 if use_splitk else 0
+    sbytes = max(M * N * 4 * 64, 8 * (M + N) * K + 4096) if use_splitk else 0
     scratch = torch.empty(sbytes, dtype=torch.uint8, device=a.device) if sbytes else None
     rc = lib.b200rnn_gemm_f32(M, N, K, a.data_ptr(), lda, int(a_kcontig), b.data_ptr(), ldb,
                               int(b_kcontig), out.data_ptr(), out.stride(0),

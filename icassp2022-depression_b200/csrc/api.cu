@@ -113,8 +113,9 @@ int make_reserve(const Dims& d, ReserveLayout* r) {
 
 // ---- scratch layout (floats) ------------------------------------------------------------------
 struct ScratchLayout {
-  // forward, inference
-  size_t f_gates[2], f_y[2];
+  // forward
+  size_t f_gates[2], f_y[2], f_tc;
+  size_t f_tc_bytes;
   size_t f_total;
   // backward
   size_t b_dgates[2], b_dghn[2], b_wt[2], b_bpart[2], b_dy, b_gemm;
@@ -131,6 +132,13 @@ void make_scratch(const Dims& d, ScratchLayout* s) {
   for (int k = 0; k < 2; ++k) {
     s->f_y[k] = off;
     off += align_up(d.TB * d.DH, ALIGN_F);
+  }
+  // split operands (hi/lo) of the tcgen05 3xTF32 input projection
+  {
+    const int Kmax = d.I > (int)d.DH ? d.I : (int)d.DH;
+    s->f_tc = off;
+    s->f_tc_bytes = gemm_tc_scratch_bytes((int)d.TB, (int)d.GH, Kmax);
+    off += align_up(s->f_tc_bytes / sizeof(float) + 1, ALIGN_F);
   }
   s->f_total = off;
 
@@ -217,8 +225,8 @@ B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_
     set_error("forward: B200RNN_FLAG_SAVE_FOR_BACKWARD needs a reserve buffer");
     return B200RNN_ERR_INVALID;
   }
-  if (!save && !scratch) {
-    set_error("forward: a scratch buffer is required when nothing is saved for backward");
+  if (!scratch) {
+    set_error("forward: a scratch buffer is required");
     return B200RNN_ERR_INVALID;
   }
   if ((reserve && !aligned_to(reserve, 256)) || (scratch && !aligned_to(scratch, 256))) {
@@ -279,6 +287,8 @@ B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_
       g.M = (int)d.TB; g.N = (int)d.GH; g.K = Il;
       g.bias1 = b_ih; g.bias2 = b_hh;
       g.bias2_n = d.mode == B200RNN_GRU ? 2 * d.H : 4 * d.H;
+      g.tc_ws = S + sl.f_tc;
+      g.tc_ws_bytes = sl.f_tc_bytes;
       rc = launch_gemm(g, nullptr, 0, st);
       if (rc) return rc;
       rp.w_hh[k] = w_hh;
@@ -471,6 +481,8 @@ B200RNN_API int b200rnn_gemm_f32(int M, int N, int K, const float* A, int64_t ld
   g.M = M; g.N = N; g.K = K;
   g.bias1 = bias;
   g.accumulate = accumulate;
+  g.tc_ws = scratch;  // used by the tcgen05 3xTF32 path when the problem is eligible and the buffer is large enough
+  g.tc_ws_bytes = scratch_bytes;
   return launch_gemm(g, scratch, scratch_bytes, static_cast<cudaStream_t>(stream_));
 }
 

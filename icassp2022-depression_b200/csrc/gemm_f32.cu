@@ -269,6 +269,7 @@ int launch_gemm(const GemmParams& p, void* scratch, size_t scratch_bytes, cudaSt
     set_error("gemm: null operand");
     return B200RNN_ERR_INVALID;
   }
+  if (p.tc_ws && gemm_tc_eligible(p, p.tc_ws_bytes)) return launch_gemm_tc(p, p.tc_ws, p.tc_ws_bytes, stream);
   GemmDev d;
   d.A = p.A; d.a_rows = p.a_rows;
   d.B = p.B; d.b_rows = p.b_rows;

@@ -19,7 +19,15 @@ struct GemmParams {
   const float* bias2;
   int bias2_n;
   int accumulate;
+  // optional workspace for the tcgen05 3xTF32 path (gemm_tc.cu); NULL => fp32 FFMA path
+  void* tc_ws;
+  size_t tc_ws_bytes;
 };
+
+// tcgen05 3xTF32 path: C = A[M,K] * B[N,K]^T + biases (both operands k-contiguous, K % 32 == 0, N % 128 == 0)
+size_t gemm_tc_scratch_bytes(int M, int N, int K);
+bool gemm_tc_eligible(const GemmParams& p, size_t ws_bytes);
+int launch_gemm_tc(const GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // bytes of scratch launch_gemm may use for split-K partials for this problem (0 if none wanted)
 size_t gemm_scratch_bytes(int M, int N, int K);

@@ -1,0 +1,368 @@
+// gemm_tc.cu — tensor-core path of the time-parallel input projection (K1):
+//     C[M,N] = A[M,K] * W[N,K]^T + bias          fp32 in / fp32 out, 3xTF32 on tcgen05
+//
+// The hidden x input gate contraction over ALL time steps at once is the one genuinely dense GEMM of the path
+// (M = B*T up to 15360, N = G*H, K = I), so it goes to the 5th-generation tensor cores — but the reference
+// arithmetic is fp32 (torch rnn.py:1221-1224 / :842-847) and parity is judged at 1e-5, which plain TF32
+// (10-bit mantissa) cannot hold. Each operand is therefore split x = hi + lo with hi = rna_tf32(x),
+// lo = x - hi (exact), and three MMAs accumulate hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator
+// (the dropped lo*lo term is ~2^-22 relative).
+// The tensor core adds into the fp32 TMEM accumulator with truncation (round toward zero), a bias of about half an
+// ulp per MMA that grows linearly with the number of MMAs chained on one accumulator (measured: 1.5e-5 abs at
+// K=1024 with a single accumulator). So the chain is cut: k-blocks go round-robin to NMAIN=3 accumulators for
+// hi*hi, the small cross terms get their own, and the epilogue adds the four with ordinary round-to-nearest fp32.
+// Resulting error ~1e-6 relative to the largest output, same order as fp32 FFMA.
+//
+// Kernel anatomy (one 128x128 output tile per CTA, 256 threads):
+//   warp 0   : TMA producer  — cp.async.bulk.tensor 2-D tiles (128 rows x 32 fp32 = 128-byte swizzled rows) of
+//              A_hi, A_lo, W_hi, W_lo into a 3-stage shared-memory ring, mbarrier complete_tx
+//   warp 1   : MMA issuer    — one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M128 N128 K8), 12 per
+//              stage, accumulator in TMEM; tcgen05.commit releases the stage / signals the epilogue
+//   warp 2   : TMEM allocator (128 columns) / deallocator
+//   warps 4-7: epilogue      — tcgen05.ld 32x32b.x16 -> registers, + folded biases, coalesced-per-row stores
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
+#include <mutex>
+
+#include "gemm_f32.cuh"
+#include "profile.cuh"
+#include "ptx.cuh"
+
+namespace b200rnn {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;        // 16 KB, both A and W tiles (BM == BN)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi, A_lo, W_hi, W_lo
+constexpr int TC_THREADS = 256;
+constexpr int TC_SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int NMAIN = 3;                       // hi*hi accumulators (k-blocks round-robin), + 1 for the cross terms
+constexpr int TMEM_COLS = (NMAIN + 1) * BN;    // 512: the whole TMEM of the SM
+
+// ---- PTX wrappers specific to this kernel -----------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   ptx::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major tile, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address   [0,14)
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                             // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                             // layout type: SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=128, dense, no negate
+constexpr uint32_t IDESC_TF32_128x128 =
+    (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct TcArgs {
+  float* C;
+  RowMap c_rows;
+  int M, N, K;
+  const float* bias1;
+  const float* bias2;
+  int bias2_n;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                       const TcArgs args) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb = args.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(tfull, 1);
+    ptx::fence_mbar_init();
+    prefetch_tmap(&map_a_hi);
+    prefetch_tmap(&map_a_lo);
+    prefetch_tmap(&map_b_hi);
+    prefetch_tmap(&map_b_lo);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        unsigned char* st = base + s * STAGE_BYTES;
+        ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, kb * BK, m0, &full[s]);
+        tma_load_2d(st + 1 * TILE_BYTES, &map_a_lo, kb * BK, m0, &full[s]);
+        tma_load_2d(st + 2 * TILE_BYTES, &map_b_hi, kb * BK, n0, &full[s]);
+        tma_load_2d(st + 3 * TILE_BYTES, &map_b_lo, kb * BK, n0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        ptx::mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t st = ptx::smem_u32(base + s * STAGE_BYTES);
+        const uint64_t a_hi = make_kmajor_sw128_desc(st + 0 * TILE_BYTES);
+        const uint64_t a_lo = make_kmajor_sw128_desc(st + 1 * TILE_BYTES);
+        const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * TILE_BYTES);
+        const uint64_t b_lo = make_kmajor_sw128_desc(st + 3 * TILE_BYTES);
+        const uint32_t acc_main = tmem_base + (uint32_t)((kb % NMAIN) * BN);
+        const uint32_t acc_cross = tmem_base + (uint32_t)(NMAIN * BN);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 8 tf32 = 32 bytes along K inside the swizzle atom
+          tc_mma_tf32(acc_cross, a_lo + adv, b_hi + adv, IDESC_TF32_128x128, (kb | k) != 0 ? 1u : 0u);
+          tc_mma_tf32(acc_cross, a_hi + adv, b_lo + adv, IDESC_TF32_128x128, 1u);
+          tc_mma_tf32(acc_main, a_hi + adv, b_hi + adv, IDESC_TF32_128x128, (kb >= NMAIN || k != 0) ? 1u : 0u);
+        }
+        tc_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+      }
+      tc_commit(tfull);
+    }
+  } else if (warp >= 4) {
+    const int wq = warp & 3;  // TMEM lane quarter this warp may read
+    ptx::mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int row = m0 + wq * 32 + lane;
+    float* crow = args.C + args.c_rows.off(row < args.M ? row : 0) + n0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
+      tc_ld_x16(lane_base + (uint32_t)(NMAIN * BN), v);  // cross terms
+#pragma unroll
+      for (int a = 0; a < NMAIN; ++a) {
+        if (a < nkb) {  // accumulator a was written (uniform condition)
+          float m[16];
+          tc_ld_x16(lane_base + (uint32_t)(a * BN), m);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] += m[e];
+        }
+      }
+      if (row < args.M) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int n = n0 + c0 + e;
+          float o = v[e];
+          if (args.bias1) o += __ldg(args.bias1 + n);
+          if (args.bias2 && n < args.bias2_n) o += __ldg(args.bias2 + n);
+          v[e] = o;
+        }
+        float4* dst = reinterpret_cast<float4*>(crow + c0);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+        dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// x = hi + lo with hi = round-to-nearest TF32 (kept in a 32-bit container), lo = x - hi (exact in fp32).
+// Reads rows through a RowMap (batch_first / permuted inputs), writes two dense [M,K] matrices.
+__global__ void split_tf32_kernel(const float* __restrict__ src, RowMap rows, int M, int K, float* __restrict__ hi,
+                                  float* __restrict__ lo, int vec_ok) {
+  const size_t nvec = (size_t)M * (K / 4);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / (K / 4));
+    const int k = (int)(i - (size_t)m * (K / 4)) * 4;
+    const float* p = src + rows.off(m) + k;
+    float4 x;
+    if (vec_ok) {
+      x = __ldg(reinterpret_cast<const float4*>(p));
+    } else {
+      x = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+    }
+    float4 h, l;
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.x)); h.x = __uint_as_float(t); l.x = x.x - h.x;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.y)); h.y = __uint_as_float(t); l.y = x.y - h.y;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.z)); h.z = __uint_as_float(t); l.z = x.z - h.z;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.w)); h.w = __uint_as_float(t); l.w = x.w - h.w;
+    *reinterpret_cast<float4*>(hi + (size_t)m * K + k) = h;
+    *reinterpret_cast<float4*>(lo + (size_t)m * K + k) = l;
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encoder() {
+  static std::mutex mu;
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// dense row-major [rows, K] fp32 matrix, box = [128 rows, 32 floats], 128-byte swizzle, OOB rows read as zero
+bool make_map(CUtensorMap* map, const float* ptr, int rows, int K) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool tc_disabled() {
+  static const bool off = getenv("B200RNN_NO_TC") != nullptr;
+  return off;
+}
+
+}  // namespace
+
+size_t gemm_tc_scratch_bytes(int M, int N, int K) { return (size_t)2 * ((size_t)M + N) * K * sizeof(float) + 1024; }
+
+bool gemm_tc_eligible(const GemmParams& p, size_t ws_bytes) {
+  if (tc_disabled()) return false;
+  if (!p.a_kcontig || !p.b_kcontig || p.accumulate) return false;
+  if (p.M < 1 || p.K < BK || p.K % BK != 0 || p.N % BN != 0) return false;
+  if (ws_bytes < gemm_tc_scratch_bytes(p.M, p.N, p.K)) return false;
+  // the epilogue stores float4 along n
+  if ((reinterpret_cast<uintptr_t>(p.C) & 15u) || (p.c_rows.s_outer % 4) || (p.c_rows.s_inner % 4)) return false;
+  return get_encoder() != nullptr;
+}
+
+int launch_gemm_tc(const GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (!gemm_tc_eligible(p, ws_bytes)) {
+    set_error("gemm_tc: problem not eligible for the tcgen05 path");
+    return B200RNN_ERR_UNSUPPORTED;
+  }
+  float* a_hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  float* a_lo = a_hi + (size_t)p.M * p.K;
+  float* b_hi = a_lo + (size_t)p.M * p.K;
+  float* b_lo = b_hi + (size_t)p.N * p.K;
+  auto aligned = [](const float* q, const RowMap& r) {
+    return (reinterpret_cast<uintptr_t>(q) & 15u) == 0 && r.s_outer % 4 == 0 && r.s_inner % 4 == 0;
+  };
+  {
+    ProfScope prof(PROF_MISC, stream);
+    size_t nv = (size_t)p.M * (p.K / 4);
+    int blocks = (int)((nv + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_tf32_kernel<<<blocks, 256, 0, stream>>>(p.A, p.a_rows, p.M, p.K, a_hi, a_lo, aligned(p.A, p.a_rows) ? 1 : 0);
+    B200_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    nv = (size_t)p.N * (p.K / 4);
+    blocks = (int)((nv + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_tf32_kernel<<<blocks, 256, 0, stream>>>(p.B, p.b_rows, p.N, p.K, b_hi, b_lo, aligned(p.B, p.b_rows) ? 1 : 0);
+    B200_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  CUtensorMap m_ahi, m_alo, m_bhi, m_blo;
+  if (!make_map(&m_ahi, a_hi, p.M, p.K) || !make_map(&m_alo, a_lo, p.M, p.K) || !make_map(&m_bhi, b_hi, p.N, p.K) ||
+      !make_map(&m_blo, b_lo, p.N, p.K)) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled failed");
+    return B200RNN_ERR_CUDA;
+  }
+  static std::mutex mu;
+  static bool attr_done = false;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!attr_done) {
+      B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+      attr_done = true;
+    }
+  }
+  TcArgs a;
+  a.C = p.C; a.c_rows = p.c_rows;
+  a.M = p.M; a.N = p.N; a.K = p.K;
+  a.bias1 = p.bias1; a.bias2 = p.bias2; a.bias2_n = p.bias2_n;
+  dim3 grid(p.N / BN, (p.M + BM - 1) / BM, 1);
+  ProfScope prof(PROF_GEMM, stream);
+  gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(m_ahi, m_alo, m_bhi, m_blo, a);
+  B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return B200RNN_OK;
+}
+
+}  // namespace b200rnn

@@ -103,8 +103,8 @@ B200RNN_API int b200rnn_workspace_bytes(const b200rnn_desc* desc, size_t* reserv
  *   h_n       [L*D, B, H] contiguous (layer-major, direction-minor: l0 fwd, l0 rev, l1 fwd, ...)
  *   c_n       same shape, LSTM only (NULL for GRU)
  *   reserve   written when flags has B200RNN_FLAG_SAVE_FOR_BACKWARD (may be NULL otherwise)
- *   scratch   required when nothing is saved (inference, or the no_grad forward of
- *             fuse_net_whole.py:337 which still runs train-mode dropout)
+ *   scratch   always required (transient: split operands of the tensor-core input projection, and the
+ *             gates / layer outputs when nothing is saved, e.g. the no_grad forward of fuse_net_whole.py:337)
  *   dropout_seed / dropout_offset / rng_state : Philox4x32-10 key / counter base of the inter-layer
  *             dropout mask. If rng_state (DEVICE pointer to {seed, offset}) is non-NULL the pair is read
  *             from it on the device and the offset is advanced there, so a captured CUDA graph draws a

@@ -1,0 +1,147 @@
+"""GPU parity of the mirrored model classes (b200rnn.AudioBiLSTM / TextBiLSTM / fusion_net / MyLoss) against the
+golden fixtures recorded from the REFERENCE's own classes (oracle/make_golden.py). Logits <= 1e-4 (north_star),
+gradients <= 1e-4 relative to the largest entry of each tensor."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import params
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _close(summary, tensor, rtol, what):
+    got = params.summarize(tensor)
+    assert set(got) == set(summary), what
+    if "full" in summary:
+        scale = max(np.abs(summary["full"]).max(), 1e-30)
+        assert np.abs(got["full"] - summary["full"]).max() <= rtol * scale, what
+        return
+    scale = max(float(summary["absmax"][0]), 1e-30)
+    assert np.abs(got["head"] - summary["head"]).max() <= rtol * scale, what
+    assert np.abs(got["sample"] - summary["sample"]).max() <= rtol * scale, what
+    assert abs(float(got["abssum"][0]) - float(summary["abssum"][0])) <= rtol * float(summary["abssum"][0]) + 1e-12, what
+
+
+@pytest.mark.parametrize("case,cls_name,regression", [
+    ("audio_clf_b3_t5", "AudioBiLSTM", False),
+    ("text_clf_b3_t6", "TextBiLSTM", False),
+    ("audio_reg_b2_t3", "AudioBiLSTM", True),
+    ("text_reg_b2_t3", "TextBiLSTM", True),
+    ("c1_text_b1_t32", "TextBiLSTM", False),       # BASELINE.json configs[0]
+])
+def test_single_modal_models_match_reference_goldens(case, cls_name, regression):
+    import b200rnn
+
+    arrays, meta = load_golden(case)
+    model = getattr(b200rnn, cls_name)(meta["cfg"], regression=regression)
+    params.fill_module(model)
+    model = model.to(DEV).eval()
+    x = params.inputs_for(case, meta["shape"]).to(DEV).requires_grad_(True)
+    out = model(x)
+    B = meta["shape"][0]
+    if meta["loss"] == "ce":
+        loss = torch.nn.CrossEntropyLoss()(out, params.labels_for(case, B).to(DEV))
+    elif meta["loss"] == "l1":
+        loss = torch.nn.L1Loss()(out, (params.inputs_for(case + ":target", (B, 1)).abs() * 10).to(DEV))
+    else:
+        loss = torch.nn.SmoothL1Loss()(out, (params.inputs_for(case + ":target", (B, 1)).abs() * 10).to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert np.abs(out.detach().cpu().numpy() - arrays["out"]).max() < 1e-4
+    assert abs(loss.item() - float(arrays["loss"][0])) < 1e-4
+    _close(arrays["dx"], x.grad, 1e-4, "dx")
+    for n, p in model.named_parameters():
+        key = "grad:" + n
+        if key in arrays:
+            _close(arrays[key], p.grad, 1e-4, key)
+
+
+@pytest.mark.parametrize("case,kind", [("gru_boundary_b5_t24", "gru"), ("lstm_boundary_b5_t17", "lstm")])
+def test_rnn_boundary_matches_reference_instance(case, kind):
+    """The exact drop-in boundary: what the reference model's own nn.GRU / nn.LSTM instance produced."""
+    import b200rnn
+
+    arrays, meta = load_golden(case)
+    cls = b200rnn.AudioBiLSTM if kind == "gru" else b200rnn.TextBiLSTM
+    model = cls(meta["cfg"])
+    params.fill_module(model)
+    rnn = getattr(model, meta["attr"]).to(DEV).eval()
+    x = params.inputs_for(case, meta["shape"]).to(DEV).requires_grad_(True)
+    res = rnn(x.permute(1, 0, 2) if meta["time_major"] else x)
+    y = res[0]
+    hs = res[1] if isinstance(res[1], tuple) else (res[1],)
+    w = params.inputs_for(case + ":w", y.shape).to(DEV)
+    loss = (y * w).sum()
+    for i, h in enumerate(hs):
+        loss = loss + (h * params.inputs_for(case + f":wh{i}", h.shape).to(DEV)).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    _close(arrays["y"], y, 1e-5, "y")
+    for i, h in enumerate(hs):
+        _close(arrays[f"state{i}"], h, 1e-5, f"state{i}")
+    _close(arrays["dx"], x.grad, 1e-4, "dx")
+    for n, p in rnn.named_parameters():
+        _close(arrays["grad:" + n], p.grad, 1e-4, n)
+
+
+@pytest.mark.parametrize("case,regression", [("fuse_clf_b3_t3", False), ("fuse_reg_b3_t3", True)])
+def test_fusion_step_matches_reference_goldens(case, regression):
+    """fuse_net_whole train-step semantics from the reference's list-of-pairs input (fuse_net_whole.py:429-456)."""
+    import b200rnn
+
+    arrays, meta = load_golden(case)
+    cfg = meta["cfg"]
+    model = b200rnn.fusion_net(cfg["text_embed_size"], cfg["text_hidden_dims"], cfg["rnn_layers"], cfg["dropout"],
+                               cfg["num_classes"], cfg["audio_hidden_dims"], cfg["audio_embed_size"],
+                               regression=regression)
+    params.fill_module(model)
+    model = model.to(DEV).eval()
+    B, T = meta["B"], meta["T"]
+    audio = params.inputs_for(case + ":audio", (B, T, cfg["audio_embed_size"])).numpy()
+    text = params.inputs_for(case + ":text", (B, T, cfg["text_embed_size"])).numpy()
+    x = [[audio[i], text[i]] for i in range(B)]
+    tf, af = model.pretrained_feature(x)
+    out = model(torch.cat((tf, af), dim=1))
+    loss = b200rnn.MyLoss(cfg["text_hidden_dims"], regression=regression)(tf, af, arrays["target"].tolist(), model)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert np.abs(tf.cpu().numpy() - arrays["text_feature"]).max() < 1e-4
+    assert np.abs(af.cpu().numpy() - arrays["audio_feature"]).max() < 1e-4
+    assert np.abs(out.detach().cpu().numpy() - arrays["out"]).max() < 1e-4
+    assert abs(loss.item() - float(arrays["loss"][0])) < 1e-4
+    _close(arrays["grad:fc_final.0.weight"], model.fc_final[0].weight.grad, 1e-4, "fc_final grad")
+    assert [n for n, p in model.named_parameters() if p.grad is not None] == ["fc_final.0.weight"]
+
+
+def test_data_parallel_shards_reproduce_full_batch_gradient():
+    """Single-process DP equivalence: 8 shard gradients, mean-reduced, equal the full-batch gradient."""
+    import b200rnn
+
+    torch.manual_seed(0)
+    cfg = dict(num_classes=2, dropout=0.0, rnn_layers=2, embedding_size=256, hidden_dims=256)
+    model = b200rnn.AudioBiLSTM(cfg).to(DEV).eval()
+    x = torch.randn(32, 12, 256, device=DEV)
+    y = torch.randint(0, 2, (32,), device=DEV)
+    torch.nn.functional.cross_entropy(model(x), y).backward()
+    full = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None]).clone()
+    model.zero_grad()
+    bucket = b200rnn.GradBucket(model)     # wgrad kernels accumulate straight into the flat bucket
+    for r in range(8):
+        sl = b200rnn.shard_batch(32, r, 8)
+        (torch.nn.functional.cross_entropy(model(x[sl]), y[sl]) / 8).backward()
+    # compare parameter by parameter (unused attention_layer params stay zero in the bucket)
+    off = 0
+    k = 0
+    for p in model.parameters():
+        n = p.numel()
+        g = bucket.flat[off:off + n]
+        off += n
+        if g.abs().sum() == 0:
+            continue
+        ref = full[k:k + n]
+        k += n
+        assert (g - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-9
+    assert k == full.numel()

@@ -35,7 +35,7 @@ constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;        // 16 KB, both A and W tiles (BM == BN)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi, A_lo, W_hi, W_lo
 constexpr int TC_THREADS = 256;
-constexpr int TC_SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int TC_SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + 2 * BN * 4 /*bias*/ + 64;
 constexpr int NMAIN = 3;                       // hi*hi accumulators (k-blocks round-robin), + 1 for the cross terms
 constexpr int TMEM_COLS = (NMAIN + 1) * BN;    // 512: the whole TMEM of the SM
 
@@ -104,8 +104,14 @@ struct TcArgs {
   const float* bias1;
   const float* bias2;
   int bias2_n;
+  int tiles_m, tiles_n;
+  int nmain;  // hi*hi accumulators in use (1..NMAIN): k-blocks go round-robin over them
+  int nsets;  // TMEM accumulator sets (2 when (nmain+1)*BN*2 <= 512: epilogue of tile i overlaps mainloop of i+1)
 };
 
+// Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ... (m fastest, so consecutive tiles of a CTA mostly
+// share their W tile rows in L2). Warp roles loop independently over the same tile sequence and meet only through
+// mbarriers: smem ring full/empty (TMA <-> MMA), TMEM set full/empty (MMA <-> epilogue).
 __global__ void __launch_bounds__(TC_THREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -114,19 +120,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  uint64_t* tfull = empty + STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][BN] folded bias of the tile, per TMEM set
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int nkb = args.K / BK;
+  const int ntiles = args.tiles_m * args.tiles_n;
+  const int set_cols = (args.nmain + 1) * BN;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
     }
-    ptx::mbar_init(tfull, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull[s], 1);
+      ptx::mbar_init(&tempty[s], 4);  // one arrival per epilogue warp
+    }
     ptx::fence_mbar_init();
     prefetch_tmap(&map_a_hi);
     prefetch_tmap(&map_a_lo);
@@ -146,77 +158,104 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        ptx::mbar_wait(&empty[s], ph ^ 1);
-        unsigned char* st = base + s * STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-        tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, kb * BK, m0, &full[s]);
-        tma_load_2d(st + 1 * TILE_BYTES, &map_a_lo, kb * BK, m0, &full[s]);
-        tma_load_2d(st + 2 * TILE_BYTES, &map_b_hi, kb * BK, n0, &full[s]);
-        tma_load_2d(st + 3 * TILE_BYTES, &map_b_lo, kb * BK, n0, &full[s]);
+      int it = 0;  // running k-block counter across tiles (ring position)
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile % args.tiles_m) * BM, n0 = (tile / args.tiles_m) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          unsigned char* st = base + s * STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, kb * BK, m0, &full[s]);
+          tma_load_2d(st + 1 * TILE_BYTES, &map_a_lo, kb * BK, m0, &full[s]);
+          tma_load_2d(st + 2 * TILE_BYTES, &map_b_hi, kb * BK, n0, &full[s]);
+          tma_load_2d(st + 3 * TILE_BYTES, &map_b_lo, kb * BK, n0, &full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        ptx::mbar_wait(&full[s], ph);
+      int it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+        const int set = ti % args.nsets;
+        const uint32_t use = (uint32_t)(ti / args.nsets);  // how often this set has been used before
+        ptx::mbar_wait(&tempty[set], (use & 1) ^ 1);       // the epilogue has drained this set
         tc_fence_after();
-        const uint32_t st = ptx::smem_u32(base + s * STAGE_BYTES);
-        const uint64_t a_hi = make_kmajor_sw128_desc(st + 0 * TILE_BYTES);
-        const uint64_t a_lo = make_kmajor_sw128_desc(st + 1 * TILE_BYTES);
-        const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * TILE_BYTES);
-        const uint64_t b_lo = make_kmajor_sw128_desc(st + 3 * TILE_BYTES);
-        const uint32_t acc_main = tmem_base + (uint32_t)((kb % NMAIN) * BN);
-        const uint32_t acc_cross = tmem_base + (uint32_t)(NMAIN * BN);
+        const uint32_t acc_set = tmem_base + (uint32_t)(set * set_cols);
+        const uint32_t acc_cross = acc_set + (uint32_t)(args.nmain * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t st = ptx::smem_u32(base + s * STAGE_BYTES);
+          const uint64_t a_hi = make_kmajor_sw128_desc(st + 0 * TILE_BYTES);
+          const uint64_t a_lo = make_kmajor_sw128_desc(st + 1 * TILE_BYTES);
+          const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * TILE_BYTES);
+          const uint64_t b_lo = make_kmajor_sw128_desc(st + 3 * TILE_BYTES);
+          const uint32_t acc_main = acc_set + (uint32_t)((kb % args.nmain) * BN);
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 8 tf32 = 32 bytes along K inside the swizzle atom
-          tc_mma_tf32(acc_cross, a_lo + adv, b_hi + adv, IDESC_TF32_128x128, (kb | k) != 0 ? 1u : 0u);
-          tc_mma_tf32(acc_cross, a_hi + adv, b_lo + adv, IDESC_TF32_128x128, 1u);
-          tc_mma_tf32(acc_main, a_hi + adv, b_hi + adv, IDESC_TF32_128x128, (kb >= NMAIN || k != 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 8 tf32 = 32 bytes along K inside the swizzle atom
+            tc_mma_tf32(acc_cross, a_lo + adv, b_hi + adv, IDESC_TF32_128x128, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_tf32(acc_cross, a_hi + adv, b_lo + adv, IDESC_TF32_128x128, 1u);
+            tc_mma_tf32(acc_main, a_hi + adv, b_hi + adv, IDESC_TF32_128x128, (kb >= args.nmain || k != 0) ? 1u : 0u);
+          }
+          tc_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
         }
-        tc_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+        tc_commit(&tfull[set]);
       }
-      tc_commit(tfull);
     }
   } else if (warp >= 4) {
     const int wq = warp & 3;  // TMEM lane quarter this warp may read
-    ptx::mbar_wait(tfull, 0);
-    tc_fence_after();
-    const int row = m0 + wq * 32 + lane;
-    float* crow = args.C + args.c_rows.off(row < args.M ? row : 0) + n0;
+    const int et = threadIdx.x - 128;  // 0..127
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int m0 = (tile % args.tiles_m) * BM, n0 = (tile / args.tiles_m) * BN;
+      const int set = ti % args.nsets;
+      const uint32_t use = (uint32_t)(ti / args.nsets);
+      // folded bias of this tile's columns -> smem (issued before waiting for the accumulator)
+      {
+        const int n = n0 + et;
+        float bv = 0.f;
+        if (args.bias1) bv += __ldg(args.bias1 + n);
+        if (args.bias2 && n < args.bias2_n) bv += __ldg(args.bias2 + n);
+        bias_s[set * BN + et] = bv;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+      ptx::mbar_wait(&tfull[set], use & 1);
+      tc_fence_after();
+      const int row = m0 + wq * 32 + lane;
+      float* crow = args.C + args.c_rows.off(row < args.M ? row : 0) + n0;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(set * set_cols);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float v[16];
-      const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
-      tc_ld_x16(lane_base + (uint32_t)(NMAIN * BN), v);  // cross terms
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tc_ld_x16(lane_base + (uint32_t)(args.nmain * BN + c0), v);  // cross terms
+        for (int a = 0; a < args.nmain; ++a) {
+          if (a < nkb) {  // accumulator a was written (uniform condition)
+            float m[16];
+            tc_ld_x16(lane_base + (uint32_t)(a * BN + c0), m);
 #pragma unroll
-      for (int a = 0; a < NMAIN; ++a) {
-        if (a < nkb) {  // accumulator a was written (uniform condition)
-          float m[16];
-          tc_ld_x16(lane_base + (uint32_t)(a * BN), m);
+            for (int e = 0; e < 16; ++e) v[e] += m[e];
+          }
+        }
+        if (row < args.M) {
+          const float4* bs = reinterpret_cast<const float4*>(&bias_s[set * BN + c0]);
+          float4* dst = reinterpret_cast<float4*>(crow + c0);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] += m[e];
+          for (int q = 0; q < 4; ++q) {
+            const float4 bq = bs[q];
+            dst[q] = make_float4(v[4 * q + 0] + bq.x, v[4 * q + 1] + bq.y, v[4 * q + 2] + bq.z, v[4 * q + 3] + bq.w);
+          }
         }
       }
-      if (row < args.M) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int n = n0 + c0 + e;
-          float o = v[e];
-          if (args.bias1) o += __ldg(args.bias1 + n);
-          if (args.bias2 && n < args.bias2_n) o += __ldg(args.bias2 + n);
-          v[e] = o;
-        }
-        float4* dst = reinterpret_cast<float4*>(crow + c0);
-        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-        dst[2] = make_float4(v[8], v[9], v[10], v[11]);
-        dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+      // this warp is done reading the set: release it to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(&tempty[set])) : "memory");
       }
     }
   }
@@ -357,7 +396,20 @@ int launch_gemm_tc(const GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t 
   a.C = p.C; a.c_rows = p.c_rows;
   a.M = p.M; a.N = p.N; a.K = p.K;
   a.bias1 = p.bias1; a.bias2 = p.bias2; a.bias2_n = p.bias2_n;
-  dim3 grid(p.N / BN, (p.M + BM - 1) / BM, 1);
+  a.tiles_m = (p.M + BM - 1) / BM;
+  a.tiles_n = p.N / BN;
+  const int nkb = p.K / BK;
+  a.nmain = (nkb + 11) / 12;  // <= 12 k-blocks (48 hi*hi MMAs) chained per accumulator
+  if (a.nmain < 1) a.nmain = 1;
+  if (a.nmain > NMAIN) a.nmain = NMAIN;
+  a.nsets = ((a.nmain + 1) * BN * 2 <= TMEM_COLS) ? 2 : 1;
+  int sms = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int ntiles = a.tiles_m * a.tiles_n;
+  dim3 grid(ntiles < sms ? ntiles : sms, 1, 1);
   ProfScope prof(PROF_GEMM, stream);
   gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(m_ahi, m_alo, m_bhi, m_blo, a);
   B200_CUDA_CHECK(cudaGetLastError());

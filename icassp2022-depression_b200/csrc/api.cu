@@ -18,6 +18,7 @@ namespace b200rnn {
 
 static thread_local char g_err[512] = {0};
 static std::atomic<unsigned long long> g_launches{0};
+long long* g_trace = nullptr;  // debug hook: device buffer [T][8] for rec_fwd phase timestamps
 
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
@@ -183,6 +184,9 @@ B200RNN_API const char* b200rnn_last_error(void) { return g_err; }
 
 B200RNN_API unsigned long long b200rnn_launch_count(void) { return g_launches.load(); }
 
+/* debug only (not declared in the public header): device buffer of [T][8] int64 phase timestamps */
+B200RNN_API void b200rnn_debug_set_trace(long long* dev_buf) { g_trace = dev_buf; }
+
 B200RNN_API int b200rnn_sm_count(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -306,6 +310,7 @@ B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_
     }
     rp.h_n = h_n + (size_t)l * d.D * d.B * d.H;
     rp.c_n = c_n ? c_n + (size_t)l * d.D * d.B * d.H : nullptr;
+    rp.trace = g_trace;
     rc = launch_rec_fwd(rp, st);
     if (rc) return rc;
     if (drop && l + 1 < d.L) {  // K7; keeps the raw output when it is needed by backward, else in place

@@ -124,6 +124,55 @@ __device__ __forceinline__ void dots_chunk(const float* __restrict__ W_s, int gr
   }
 }
 
+// Same chunk contraction on the packed-fp32 pipe of sm_100 (FFMA2, PTX fma.rn.f32x2): the accumulator of every
+// (row, batch) is a float2 holding the even-k and odd-k partial sums, so one instruction retires two FMAs and the
+// operands are the naturally 64-bit aligned halves of the 16-byte shared-memory loads. Halves the FMA issue slots
+// of the time loop; fold_pairs() adds the two halves before the butterfly.
+template <int NR, int RG, int KL, int UPL, int BS, int KLEN, int VSTRIDE>
+__device__ __forceinline__ void dots_chunk2(const float* __restrict__ W_s, int group_stride, int row0,
+                                            const float (&wreg)[RG > 0 ? RG : 1][UPL][KLEN / KL],
+                                            const float* __restrict__ vec_s, int c, int ca, int lane,
+                                            float2 (&acc)[NR][UPL][BS]) {
+  using LM = LaneMap<KL, UPL, BS>;
+  const int kl = LM::kl(lane), p = LM::p(lane), q = LM::q(lane), cgrp = LM::cl(lane);
+  const int koff = ca * 4 * KL + kl * 4;
+  float4 hv[BS];
+#pragma unroll
+  for (int ab = 0; ab < BS; ++ab) hv[ab] = *reinterpret_cast<const float4*>(&vec_s[(ab ^ q) * VSTRIDE + koff]);
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+#pragma unroll
+    for (int au = 0; au < UPL; ++au) {
+      float4 wv;
+      if (r < NR - RG) {
+        const int row = r * group_stride + row0 + cgrp * UPL + (au ^ p);
+        wv = *reinterpret_cast<const float4*>(&W_s[row * KLEN + koff]);
+      } else {
+        const int ri = (r - (NR - RG)) > 0 ? (r - (NR - RG)) : 0;
+        wv = make_float4(wreg[ri][au][c * 4 + 0], wreg[ri][au][c * 4 + 1], wreg[ri][au][c * 4 + 2],
+                         wreg[ri][au][c * 4 + 3]);
+      }
+#pragma unroll
+      for (int ab = 0; ab < BS; ++ab) {
+        float2 a = acc[r][au][ab];
+        a = __ffma2_rn(make_float2(wv.x, wv.y), make_float2(hv[ab].x, hv[ab].y), a);
+        a = __ffma2_rn(make_float2(wv.z, wv.w), make_float2(hv[ab].z, hv[ab].w), a);
+        acc[r][au][ab] = a;
+      }
+    }
+  }
+}
+
+template <int NR, int UPL, int BS>
+__device__ __forceinline__ void fold_pairs(const float2 (&acc2)[NR][UPL][BS], float (&acc)[NR][UPL][BS]) {
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int au = 0; au < UPL; ++au)
+#pragma unroll
+      for (int ab = 0; ab < BS; ++ab) acc[r][au][ab] = acc2[r][au][ab].x + acc2[r][au][ab].y;
+}
+
 // Transposing butterfly over the KL k-lanes. On return acc[r][0][0] of a lane holds the full sum for
 // unit LaneMap::unit(lane), batch LaneMap::q(lane).
 template <int NR, int KL, int UPL, int BS>

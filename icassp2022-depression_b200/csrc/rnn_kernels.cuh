@@ -16,6 +16,7 @@ struct RecFwdParams {
   long long y_st, y_sb;
   float* h_n;                // [D,B,H] of this layer
   float* c_n;                // [D,B,H] of this layer (LSTM) or NULL
+  long long* trace;          // debug: per-step phase timestamps of CTA 0 / warp 0 (NULL = off), [T][8]
 };
 
 struct RecBwdParams {

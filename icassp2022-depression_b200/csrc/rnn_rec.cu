@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
   float* W_s = reinterpret_cast<float*>(smem_raw);                 // [NSM*HS][H]
   float* h_s = W_s + (size_t)NSM * HS * H;                         // [2][BS][H]
   uint64_t* bars = reinterpret_cast<uint64_t*>(h_s + 2 * BS * H);  // [0] weights, [1 + buf*C + src] state slices
-  constexpr int NCH = Cfg::NCH, CPS = Cfg::CPS, SPC = Cfg::SPC;
+  constexpr int NCH = Cfg::NCH, CPS = Cfg::CPS;
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -162,14 +162,26 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     const float* h_cur = h_s + cur * BS * H;
     float* h_nxt = h_s + nxt * BS * H;
     const uint32_t par = ((step - 1) >> 1) & 1;
+#ifdef B200RNN_TRACE
+    const bool tr = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
+#else
+    constexpr bool tr = false;  // build with -DB200RNN_TRACE for the per-phase clock64 timeline (tools/trace_rec.py)
+#endif
+    long long* trow = p.trace + (size_t)step * 8;
+    if (tr) trow[0] = clock64();
 
+    constexpr bool PACK2 = (MODE == B200RNN_GRU);  // FFMA2 pays off only where the register budget allows it
+    float2 acc2[PACK2 ? G : 1][UPL][BS];
     float acc[G][UPL][BS];
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
       for (int au = 0; au < UPL; ++au)
 #pragma unroll
-        for (int ab = 0; ab < BS; ++ab) acc[g][au][ab] = 0.f;
+        for (int ab = 0; ab < BS; ++ab) {
+          acc[g][au][ab] = 0.f;
+          if (PACK2) acc2[g][au][ab] = make_float2(0.f, 0.f);
+        }
     // contraction over h, one chunk at a time, starting with the slice this CTA produced itself; a chunk is
     // touched only after the slice(s) it belongs to have arrived (per-source mbarriers)
 #pragma unroll
@@ -180,18 +192,25 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
           if (c % CPS == 0) ptx::mbar_wait(&bars[1 + cur * C + ca / CPS], par);
         } else {
 #pragma unroll
-          for (int s2 = 0; s2 < SPC; ++s2) ptx::mbar_wait(&bars[1 + cur * C + ca * SPC + s2], par);
+          for (int s2 = 0; s2 < Cfg::SPC; ++s2) ptx::mbar_wait(&bars[1 + cur * C + ca * Cfg::SPC + s2], par);
         }
       }
-      dots_chunk<G, RG, KL, UPL, BS, H, H>(W_s, HS, w * UPW, wreg, h_cur, c, ca, lane, acc);
+      if (tr && c == NCH - 1) trow[1] = clock64();  // all slices of h_step have arrived
+      if constexpr (PACK2)
+        dots_chunk2<G, RG, KL, UPL, BS, H, H>(W_s, HS, w * UPW, wreg, h_cur, c, ca, lane, acc2);
+      else
+        dots_chunk<G, RG, KL, UPL, BS, H, H>(W_s, HS, w * UPW, wreg, h_cur, c, ca, lane, acc);
     }
+    if (tr) trow[2] = clock64();
     // every slice of h_step has been consumed by this thread => the barriers of the other buffer are re-armed
     if (tid == 0 && step + 1 < T) {
 #pragma unroll
       for (int src = 0; src < C; ++src)
         ptx::mbar_arrive_expect_tx(&bars[1 + nxt * C + src], (uint32_t)(BS * HS * sizeof(float)));
     }
+    if constexpr (PACK2) fold_pairs<G, UPL, BS>(acc2, acc);
     warp_transpose_reduce<G, KL, UPL, BS>(acc);
+    if (tr) trow[3] = clock64() + (long long)(acc[0][0][0] == 12345.678f);  // value dependence pins the order
 
     float hnew, s0, s1, s2, s3 = 0.f, sx;
     if (MODE == B200RNN_GRU) {
@@ -212,9 +231,11 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
       s0 = ig; s1 = fg; s2 = gg; s3 = og; sx = cnew;
     }
     h_prev = hnew;
+    if (tr) trow[4] = clock64() + (long long)(hnew == 12345.678f);
 
     if (step + 1 < T)
       allgather_units<C, KL, UPL, BS>(hnew, h_nxt, H, j0 + w * UPW, &bars[1 + nxt * C + rank], lane);
+    if (tr) trow[5] = clock64();
 
     // off the critical path: global stores of this step, prefetch of the next step's x-projection
     if (valid) {
@@ -536,6 +557,10 @@ bool try_fwd(const RecFwdParams& p, cudaStream_t s, bool force, int* rc) {
   auto k = rec_fwd_kernel<MODE, H, C, BS, KL, UPL, RG>;
   const int nslices = (p.B + BS - 1) / BS;
   const int nclusters = nslices * p.D;
+  static const bool debug = getenv("B200RNN_DEBUG") != nullptr;
+  if (debug)
+    fprintf(stderr, "[b200rnn] fwd cfg C=%d BS=%d KL=%d UPL=%d RG=%d: need %d clusters, capacity %d, smem %zu\n", C, BS,
+            KL, UPL, RG, nclusters, max_active_clusters(k, C, Cfg::NT, Cfg::FWD_SMEM), (size_t)Cfg::FWD_SMEM);
   if (!force && nclusters > max_active_clusters(k, C, Cfg::NT, Cfg::FWD_SMEM)) return false;
   *rc = launch_clustered(k, p, nslices, nclusters, C, Cfg::NT, Cfg::FWD_SMEM, s, PROF_REC_FWD);
   return true;
@@ -589,6 +614,8 @@ int launch_rec_fwd(const RecFwdParams& p, cudaStream_t s) {
     } else if (variant == 3) {
       try_fwd<B200RNN_GRU, 256, 8, 8, 32, 4, 1>(p, s, true, &rc);
       return rc;
+    } else if (variant == 4) {  // 128-thread CTAs, two per SM: two independent recurrences overlap their latency
+      if (try_fwd<B200RNN_GRU, 256, 8, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
     } else {  // default: measured fastest on B200 (232 us for B=128, T=120)
       if (try_fwd<B200RNN_GRU, 256, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
     }
@@ -606,6 +633,7 @@ int launch_rec_fwd(const RecFwdParams& p, cudaStream_t s) {
     return rc;
   }
   if (p.mode == B200RNN_LSTM && p.H == 128) {
+    if (variant == 4 && try_fwd<B200RNN_LSTM, 128, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
     if (try_fwd<B200RNN_LSTM, 128, 2, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
     try_fwd<B200RNN_LSTM, 128, 4, 8, 16, 2, 1>(p, s, true, &rc);
     return rc;

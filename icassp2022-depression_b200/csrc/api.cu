@@ -121,6 +121,10 @@ struct ScratchLayout {
   // backward
   size_t b_dgates[2], b_dghn[2], b_wt[2], b_bpart[2], b_dy, b_gemm;
   size_t b_gemm_bytes;
+  // tcgen05 backward GEMMs: split / transposed-split operands (hi at the offset, lo right behind it)
+  size_t b_tc_dg, b_tc_dgT, b_tc_hnT, b_tc_xT, b_tc_yT, b_tc_wT, b_tc_part;
+  size_t b_tc_part_bytes;
+  long long b_ldk;  // leading dimension of the transposed operands: T*B rounded up to a multiple of 4
   size_t b_total;
 };
 
@@ -166,6 +170,20 @@ void make_scratch(const Dims& d, ScratchLayout* s) {
   s->b_gemm = off;
   s->b_gemm_bytes = gb;
   off += align_up(gb / sizeof(float) + 1, ALIGN_F);
+  {
+    const size_t Imax = d.I > (int)d.DH ? (size_t)d.I : d.DH;
+    const size_t ldk = (d.TB + 3) / 4 * 4;
+    s->b_ldk = (long long)ldk;
+    s->b_tc_dg = off;   off += align_up(2 * d.TB * d.GH, ALIGN_F);
+    s->b_tc_dgT = off;  off += align_up(2 * d.GH * ldk, ALIGN_F);
+    s->b_tc_hnT = off;  off += align_up(2 * (size_t)d.H * ldk, ALIGN_F);
+    s->b_tc_xT = off;   off += align_up(2 * Imax * ldk, ALIGN_F);
+    s->b_tc_yT = off;   off += align_up(2 * (size_t)d.H * ldk, ALIGN_F);
+    s->b_tc_wT = off;   off += align_up(2 * Imax * d.GH, ALIGN_F);
+    s->b_tc_part = off;
+    s->b_tc_part_bytes = (size_t)160 * 128 * 128 * sizeof(float);  // <= (#SMs / tiles) * M * N
+    off += align_up(s->b_tc_part_bytes / sizeof(float), ALIGN_F);
+  }
   s->b_total = off;
 }
 
@@ -393,6 +411,14 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
       in_rows = simple_rows((long long)d.DH);
     }
     const bool want_dx = (l > 0) || (dx != nullptr);
+    // ---- tcgen05 3xTF32 path for the wgrad / dgrad GEMMs (falls back to the FFMA kernel per GEMM) -------------
+    const long long ldk = sl.b_ldk;
+    const bool tc_l = tc_available() && (Il % 128 == 0);
+    float* xT = S + sl.b_tc_xT;  // [Il][ldk] hi, then lo
+    if (tc_l) {  // X_l^T, shared by both directions
+      rc = tc_split_transpose(in, in_rows, (int)d.TB, Il, xT, xT + (size_t)Il * ldk, ldk, st);
+      if (rc) return rc;
+    }
     for (int k = 0; k < d.D; ++k) {
       const float* const* pp = params + (size_t)(l * d.D + k) * 4;
       float* const* gp = dparams + (size_t)(l * d.D + k) * 4;
@@ -403,7 +429,77 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
         rc = launch_bias_reduce(S + sl.b_bpart[k], bp.nslices_out, d.mode, d.H, db_ih, db_hh, accumulate, st);
         if (rc) return rc;
       }
-      if (dw_ih) {  // dW_ih = dGi^T * X_l
+      bool done_dwih = (dw_ih == nullptr), done_dwhh = (dw_hh == nullptr), done_dx = !want_dx;
+      if (tc_l) {
+        float* dGT = S + sl.b_tc_dgT;  // [GH][ldk]
+        float* hnT = S + sl.b_tc_hnT;  // [H][ldk]   (GRU: dn * r)
+        const TcOperand opX{xT, xT + (size_t)Il * ldk, ldk};
+        if (dw_ih || dw_hh) {
+          rc = tc_split_transpose(dG, simple_rows((long long)d.GH), (int)d.TB, (int)d.GH, dGT, dGT + d.GH * ldk, ldk, st);
+          if (rc) return rc;
+        }
+        if (dw_ih) {  // dW_ih[GH, Il] = dGi^T[GH, TB] * X_l^T[Il, TB]^T
+          const TcOperand opA{dGT, dGT + d.GH * ldk, ldk};
+          rc = tc_gemm_presplit(opA, opX, (int)d.GH, Il, (int)d.TB, dw_ih, simple_rows(Il), nullptr, nullptr, 0,
+                                accumulate, S + sl.b_tc_part, sl.b_tc_part_bytes, st);
+          if (rc) return rc;
+          done_dwih = true;
+        }
+        if (dw_hh && d.T > 1 && d.B % 4 == 0) {
+          // dW_hh = sum_t dGh[t]^T h_{prev(t)}: columns of the transposed operands are (t,b) flattened time-major,
+          // so the one-step shift is a column offset of B (forward: dG[t] with y[t-1]; reverse: dG[t] with y[t+1])
+          float* yT = S + sl.b_tc_yT;  // [H][ldk]
+          rc = tc_split_transpose(bp.y + (long long)k * d.H, tb_rows(bp.y_st, bp.y_sb, d.B), (int)d.TB, d.H, yT,
+                                  yT + (size_t)d.H * ldk, ldk, st);
+          if (rc) return rc;
+          const int Kp = (d.T - 1) * d.B;
+          const size_t offA = (k == 0) ? (size_t)d.B : 0, offY = (k == 0) ? 0 : (size_t)d.B;
+          const TcOperand opY{yT + offY, yT + (size_t)d.H * ldk + offY, ldk};
+          if (d.mode == B200RNN_LSTM) {
+            const TcOperand opA{dGT + offA, dGT + d.GH * ldk + offA, ldk};
+            rc = tc_gemm_presplit(opA, opY, (int)d.GH, d.H, Kp, dw_hh, simple_rows(d.H), nullptr, nullptr, 0,
+                                  accumulate, S + sl.b_tc_part, sl.b_tc_part_bytes, st);
+            if (rc) return rc;
+          } else {
+            rc = tc_split_transpose(dHN, simple_rows((long long)d.H), (int)d.TB, d.H, hnT, hnT + (size_t)d.H * ldk, ldk, st);
+            if (rc) return rc;
+            const TcOperand opRZ{dGT + offA, dGT + d.GH * ldk + offA, ldk};  // rows [0, 2H): r and z gates
+            rc = tc_gemm_presplit(opRZ, opY, 2 * d.H, d.H, Kp, dw_hh, simple_rows(d.H), nullptr, nullptr, 0,
+                                  accumulate, S + sl.b_tc_part, sl.b_tc_part_bytes, st);
+            if (rc) return rc;
+            const TcOperand opN{hnT + offA, hnT + (size_t)d.H * ldk + offA, ldk};  // n rows use dn * r
+            rc = tc_gemm_presplit(opN, opY, d.H, d.H, Kp, dw_hh + (size_t)2 * d.H * d.H, simple_rows(d.H), nullptr,
+                                  nullptr, 0, accumulate, S + sl.b_tc_part, sl.b_tc_part_bytes, st);
+            if (rc) return rc;
+          }
+          done_dwhh = true;
+        }
+        if (want_dx) {  // dX_l (+)= dGi[TB, GH] * W_ih[GH, Il]
+          float* Cx;
+          RowMap cx_rows;
+          if (l == 0) {
+            Cx = dx; cx_rows = tb_rows(dxs_t, dxs_b, d.B);
+          } else {
+            Cx = S + sl.b_dy; cx_rows = simple_rows((long long)d.DH);
+          }
+          const bool ok = (reinterpret_cast<uintptr_t>(Cx) % 16 == 0) && cx_rows.s_outer % 4 == 0 && cx_rows.s_inner % 4 == 0;
+          if (ok) {
+            float* dGs = S + sl.b_tc_dg;  // [TB][GH]
+            float* wT = S + sl.b_tc_wT;   // [Il][GH]
+            rc = tc_split(dG, simple_rows((long long)d.GH), (int)d.TB, (int)d.GH, dGs, dGs + d.TB * d.GH, st);
+            if (rc) return rc;
+            rc = tc_split_transpose(pp[0], simple_rows(Il), (int)d.GH, Il, wT, wT + (size_t)Il * d.GH, (long long)d.GH, st);
+            if (rc) return rc;
+            const TcOperand opA{dGs, dGs + d.TB * d.GH, (long long)d.GH};
+            const TcOperand opB{wT, wT + (size_t)Il * d.GH, (long long)d.GH};
+            rc = tc_gemm_presplit(opA, opB, (int)d.TB, Il, (int)d.GH, Cx, cx_rows, nullptr, nullptr, 0, (k > 0) ? 1 : 0,
+                                  nullptr, 0, st);
+            if (rc) return rc;
+            done_dx = true;
+          }
+        }
+      }
+      if (!done_dwih) {  // dW_ih = dGi^T * X_l
         GemmParams g;
         memset(&g, 0, sizeof(g));
         g.A = dG; g.a_rows = simple_rows((long long)d.GH); g.a_kcontig = 0;
@@ -414,7 +510,7 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
         rc = launch_gemm(g, gemm_ws, sl.b_gemm_bytes, st);
         if (rc) return rc;
       }
-      if (dw_hh) {  // dW_hh = sum_t dGh[t]^T * h_{prev(t)}   (h_prev of the first scanned step is 0)
+      if (!done_dwhh) {  // dW_hh = sum_t dGh[t]^T * h_{prev(t)}   (h_prev of the first scanned step is 0)
         const int Kp = (d.T - 1) * d.B;
         // forward direction: pairs (dG[t], y[t-1]) for t = 1..T-1 ; reverse: (dG[t], y[t+1]) for t = 0..T-2
         const size_t g_t0 = (k == 0) ? (size_t)d.B : 0;  // first dG row
@@ -447,7 +543,7 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
           if (rc) return rc;
         }
       }
-      if (want_dx) {  // dX_l (+)= dGi * W_ih
+      if (!done_dx) {  // dX_l (+)= dGi * W_ih
         GemmParams g;
         memset(&g, 0, sizeof(g));
         g.A = dG; g.a_rows = simple_rows((long long)d.GH); g.a_kcontig = 1;

@@ -252,6 +252,18 @@ void launch_tile(const GemmDev& d, bool a_kc, bool b_kc, dim3 grid, cudaStream_t
 
 }  // namespace
 
+int launch_splitk_reduce(const float* partial, int splitk, int M, int N, float* C, const RowMap& c_rows,
+                         const float* bias1, const float* bias2, int bias2_n, int accumulate, cudaStream_t stream) {
+  size_t total = (size_t)M * N;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, splitk, M, N, C, c_rows, bias1, bias2, bias2_n, accumulate);
+  B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return B200RNN_OK;
+}
+
 size_t gemm_scratch_bytes(int M, int N, int K) {
   // worst case the planner may want: up to 296 tiles' worth of splits, bounded by K/256
   const long t64 = (long)((M + 63) / 64) * ((N + 63) / 64);

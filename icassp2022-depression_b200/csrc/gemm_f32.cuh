@@ -29,6 +29,23 @@ size_t gemm_tc_scratch_bytes(int M, int N, int K);
 bool gemm_tc_eligible(const GemmParams& p, size_t ws_bytes);
 int launch_gemm_tc(const GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+// Building blocks of the tcgen05 path for callers that manage the split operands themselves (backward pass).
+struct TcOperand {
+  const float* hi;
+  const float* lo;
+  long long ld;  // floats between consecutive rows of the K-major [rows, K] matrices (multiple of 4)
+};
+bool tc_available();
+int tc_split(const float* src, const RowMap& rows, int R, int Cc, float* hi, float* lo, cudaStream_t stream);
+int tc_split_transpose(const float* src, const RowMap& rows, int R, int Cc, float* hiT, float* loT, long long ldT,
+                       cudaStream_t stream);
+int tc_gemm_presplit(const TcOperand& A, const TcOperand& B, int M, int N, int K, float* C, const RowMap& c_rows,
+                     const float* bias1, const float* bias2, int bias2_n, int accumulate, void* splitk_ws,
+                     size_t splitk_ws_bytes, cudaStream_t stream);
+// C(m,n) (+)= sum_z partial[z][m][n] (+ biases), fixed order (deterministic)
+int launch_splitk_reduce(const float* partial, int splitk, int M, int N, float* C, const RowMap& c_rows,
+                         const float* bias1, const float* bias2, int bias2_n, int accumulate, cudaStream_t stream);
+
 // bytes of scratch launch_gemm may use for split-K partials for this problem (0 if none wanted)
 size_t gemm_scratch_bytes(int M, int N, int K);
 

@@ -107,6 +107,10 @@ struct TcArgs {
   int tiles_m, tiles_n;
   int nmain;  // hi*hi accumulators in use (1..NMAIN): k-blocks go round-robin over them
   int nsets;  // TMEM accumulator sets (2 when (nmain+1)*BN*2 <= 512: epilogue of tile i overlaps mainloop of i+1)
+  int accumulate;   // C += result (splitk == 1 only)
+  int splitk;       // > 1: work item = (k-split, tile); raw partial sums go to partial[ks][M][N]
+  int kb_per_split; // k-blocks per split
+  float* partial;
 };
 
 // Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ... (m fastest, so consecutive tiles of a CTA mostly
@@ -126,8 +130,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][BN] folded bias of the tile, per TMEM set
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = args.K / BK;
+  const int nkb_total = (args.K + BK - 1) / BK;  // TMA zero-fills the K tail
   const int ntiles = args.tiles_m * args.tiles_n;
+  const int nitems = ntiles * args.splitk;
   const int set_cols = (args.nmain + 1) * BN;
 
   if (warp == 0 && lane == 0) {
@@ -159,9 +164,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;  // running k-block counter across tiles (ring position)
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tile = item % ntiles, ks = item / ntiles;
         const int m0 = (tile % args.tiles_m) * BM, n0 = (tile / args.tiles_m) * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int kb0 = ks * args.kb_per_split;
+        const int kb1 = min(nkb_total, kb0 + args.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           ptx::mbar_wait(&empty[s], ph ^ 1);
@@ -177,7 +185,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   } else if (warp == 1) {
     if (lane == 0) {
       int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ti) {
+        const int nkb = min(nkb_total, (item / ntiles + 1) * args.kb_per_split) - (item / ntiles) * args.kb_per_split;
         const int set = ti % args.nsets;
         const uint32_t use = (uint32_t)(ti / args.nsets);  // how often this set has been used before
         ptx::mbar_wait(&tempty[set], (use & 1) ^ 1);       // the epilogue has drained this set
@@ -211,7 +220,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int wq = warp & 3;  // TMEM lane quarter this warp may read
     const int et = threadIdx.x - 128;  // 0..127
     int ti = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ti) {
+      const int tile = item % ntiles, ks = item / ntiles;
+      const int nkb = min(nkb_total, (ks + 1) * args.kb_per_split) - ks * args.kb_per_split;
       const int m0 = (tile % args.tiles_m) * BM, n0 = (tile / args.tiles_m) * BN;
       const int set = ti % args.nsets;
       const uint32_t use = (uint32_t)(ti / args.nsets);
@@ -219,15 +230,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       {
         const int n = n0 + et;
         float bv = 0.f;
-        if (args.bias1) bv += __ldg(args.bias1 + n);
-        if (args.bias2 && n < args.bias2_n) bv += __ldg(args.bias2 + n);
+        if (args.splitk == 1) {
+          if (args.bias1) bv += __ldg(args.bias1 + n);
+          if (args.bias2 && n < args.bias2_n) bv += __ldg(args.bias2 + n);
+        }
         bias_s[set * BN + et] = bv;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
       ptx::mbar_wait(&tfull[set], use & 1);
       tc_fence_after();
       const int row = m0 + wq * 32 + lane;
-      float* crow = args.C + args.c_rows.off(row < args.M ? row : 0) + n0;
+      float* crow = (args.splitk > 1)
+                        ? args.partial + ((size_t)ks * args.M + (row < args.M ? row : 0)) * args.N + n0
+                        : args.C + args.c_rows.off(row < args.M ? row : 0) + n0;
       const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(set * set_cols);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -247,7 +262,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 bq = bs[q];
-            dst[q] = make_float4(v[4 * q + 0] + bq.x, v[4 * q + 1] + bq.y, v[4 * q + 2] + bq.z, v[4 * q + 3] + bq.w);
+            float4 o = make_float4(v[4 * q + 0] + bq.x, v[4 * q + 1] + bq.y, v[4 * q + 2] + bq.z, v[4 * q + 3] + bq.w);
+            if (args.accumulate && args.splitk == 1) {
+              const float4 old = dst[q];
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            dst[q] = o;
           }
         }
       }
@@ -294,6 +314,34 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, RowMap rows, in
   }
 }
 
+// Transposing variant: src [R rows (RowMap), Cc columns]  ->  hiT / loT [Cc][ldT] (element (c, r) at c*ldT + r).
+// Turns the "MN-major" operands of the wgrad GEMMs (dG^T, X^T, H_prev^T) into the K-major form the kernel takes.
+__global__ void split_tf32_transpose_kernel(const float* __restrict__ src, RowMap rows, int R, int Cc,
+                                            float* __restrict__ hiT, float* __restrict__ loT, long long ldT) {
+  __shared__ float tile[32][33];
+  const int tiles_r = (R + 31) / 32, tiles_c = (Cc + 31) / 32;
+  for (int tix = blockIdx.x; tix < tiles_r * tiles_c; tix += gridDim.x) {
+    const int tr = tix / tiles_c, tcn = tix - tr * tiles_c;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int r = tr * 32 + i, c = tcn * 32 + threadIdx.x;
+      tile[i][threadIdx.x] = (r < R && c < Cc) ? __ldg(src + rows.off(r) + c) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = tcn * 32 + i, r = tr * 32 + threadIdx.x;
+      if (c < Cc && r < R) {
+        const float x = tile[threadIdx.x][i];
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+        const float h = __uint_as_float(t);
+        hiT[(size_t)c * ldT + r] = h;
+        loT[(size_t)c * ldT + r] = x - h;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -318,11 +366,12 @@ EncodeTiledFn get_encoder() {
 }
 
 // dense row-major [rows, K] fp32 matrix, box = [128 rows, 32 floats], 128-byte swizzle, OOB rows read as zero
-bool make_map(CUtensorMap* map, const float* ptr, int rows, int K) {
+bool make_map(CUtensorMap* map, const float* ptr, int rows, int K, long long ld = 0) {
   EncodeTiledFn enc = get_encoder();
   if (!enc) return false;
+  if (ld == 0) ld = K;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
@@ -350,37 +399,49 @@ bool gemm_tc_eligible(const GemmParams& p, size_t ws_bytes) {
   return get_encoder() != nullptr;
 }
 
-int launch_gemm_tc(const GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  if (!gemm_tc_eligible(p, ws_bytes)) {
-    set_error("gemm_tc: problem not eligible for the tcgen05 path");
+int tc_split(const float* src, const RowMap& rows, int R, int Cc, float* hi, float* lo, cudaStream_t stream) {
+  const bool vec = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && rows.s_outer % 4 == 0 && rows.s_inner % 4 == 0;
+  size_t nv = (size_t)R * (Cc / 4);
+  int blocks = (int)((nv + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  ProfScope prof(PROF_MISC, stream);
+  split_tf32_kernel<<<blocks, 256, 0, stream>>>(src, rows, R, Cc, hi, lo, vec ? 1 : 0);
+  B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return B200RNN_OK;
+}
+
+int tc_split_transpose(const float* src, const RowMap& rows, int R, int Cc, float* hiT, float* loT, long long ldT,
+                       cudaStream_t stream) {
+  int tiles = ((R + 31) / 32) * ((Cc + 31) / 32);
+  int blocks = tiles < 148 * 8 ? tiles : 148 * 8;
+  if (blocks < 1) blocks = 1;
+  ProfScope prof(PROF_MISC, stream);
+  split_tf32_transpose_kernel<<<blocks, dim3(32, 8), 0, stream>>>(src, rows, R, Cc, hiT, loT, ldT);
+  B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return B200RNN_OK;
+}
+
+bool tc_available() { return !tc_disabled() && get_encoder() != nullptr; }
+
+// C[M,N] (+)= A[M,K] * B[N,K]^T (+ biases), operands already split into hi/lo K-major matrices.
+int tc_gemm_presplit(const TcOperand& A, const TcOperand& B, int M, int N, int K, float* C, const RowMap& c_rows,
+                     const float* bias1, const float* bias2, int bias2_n, int accumulate, void* splitk_ws,
+                     size_t splitk_ws_bytes, cudaStream_t stream) {
+  if (M < 1 || N % BN != 0 || K < 1) {
+    set_error("tc_gemm: unsupported shape M=%d N=%d K=%d", M, N, K);
     return B200RNN_ERR_UNSUPPORTED;
   }
-  float* a_hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  float* a_lo = a_hi + (size_t)p.M * p.K;
-  float* b_hi = a_lo + (size_t)p.M * p.K;
-  float* b_lo = b_hi + (size_t)p.N * p.K;
-  auto aligned = [](const float* q, const RowMap& r) {
-    return (reinterpret_cast<uintptr_t>(q) & 15u) == 0 && r.s_outer % 4 == 0 && r.s_inner % 4 == 0;
-  };
-  {
-    ProfScope prof(PROF_MISC, stream);
-    size_t nv = (size_t)p.M * (p.K / 4);
-    int blocks = (int)((nv + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    split_tf32_kernel<<<blocks, 256, 0, stream>>>(p.A, p.a_rows, p.M, p.K, a_hi, a_lo, aligned(p.A, p.a_rows) ? 1 : 0);
-    B200_CUDA_CHECK(cudaGetLastError());
-    count_launch();
-    nv = (size_t)p.N * (p.K / 4);
-    blocks = (int)((nv + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    split_tf32_kernel<<<blocks, 256, 0, stream>>>(p.B, p.b_rows, p.N, p.K, b_hi, b_lo, aligned(p.B, p.b_rows) ? 1 : 0);
-    B200_CUDA_CHECK(cudaGetLastError());
-    count_launch();
+  if ((reinterpret_cast<uintptr_t>(C) & 15u) || (c_rows.s_outer % 4) || (c_rows.s_inner % 4)) {
+    set_error("tc_gemm: output must be 16-byte aligned with row strides that are multiples of 4 floats");
+    return B200RNN_ERR_UNSUPPORTED;
   }
   CUtensorMap m_ahi, m_alo, m_bhi, m_blo;
-  if (!make_map(&m_ahi, a_hi, p.M, p.K) || !make_map(&m_alo, a_lo, p.M, p.K) || !make_map(&m_bhi, b_hi, p.N, p.K) ||
-      !make_map(&m_blo, b_lo, p.N, p.K)) {
-    set_error("gemm_tc: cuTensorMapEncodeTiled failed");
+  if (!make_map(&m_ahi, A.hi, M, K, A.ld) || !make_map(&m_alo, A.lo, M, K, A.ld) || !make_map(&m_bhi, B.hi, N, K, B.ld) ||
+      !make_map(&m_blo, B.lo, N, K, B.ld)) {
+    set_error("tc_gemm: cuTensorMapEncodeTiled failed (operands must be 16-byte aligned, ld %% 4 == 0)");
     return B200RNN_ERR_CUDA;
   }
   static std::mutex mu;
@@ -392,29 +453,64 @@ int launch_gemm_tc(const GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t 
       attr_done = true;
     }
   }
-  TcArgs a;
-  a.C = p.C; a.c_rows = p.c_rows;
-  a.M = p.M; a.N = p.N; a.K = p.K;
-  a.bias1 = p.bias1; a.bias2 = p.bias2; a.bias2_n = p.bias2_n;
-  a.tiles_m = (p.M + BM - 1) / BM;
-  a.tiles_n = p.N / BN;
-  const int nkb = p.K / BK;
-  a.nmain = (nkb + 11) / 12;  // <= 12 k-blocks (48 hi*hi MMAs) chained per accumulator
-  if (a.nmain < 1) a.nmain = 1;
-  if (a.nmain > NMAIN) a.nmain = NMAIN;
-  a.nsets = ((a.nmain + 1) * BN * 2 <= TMEM_COLS) ? 2 : 1;
   int sms = 148;
   {
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  TcArgs a;
+  a.C = C; a.c_rows = c_rows;
+  a.M = M; a.N = N; a.K = K;
+  a.bias1 = bias1; a.bias2 = bias2; a.bias2_n = bias2_n;
+  a.accumulate = accumulate;
+  a.tiles_m = (M + BM - 1) / BM;
+  a.tiles_n = N / BN;
   const int ntiles = a.tiles_m * a.tiles_n;
-  dim3 grid(ntiles < sms ? ntiles : sms, 1, 1);
-  ProfScope prof(PROF_GEMM, stream);
-  gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(m_ahi, m_alo, m_bhi, m_blo, a);
-  B200_CUDA_CHECK(cudaGetLastError());
-  count_launch();
+  const int nkb = (K + BK - 1) / BK;
+  // split-K when the tile count cannot fill the chip and K is long (the wgrad shapes: K = T*B)
+  int splitk = 1;
+  if (splitk_ws && ntiles * 2 <= sms && nkb >= 16) {
+    splitk = sms / ntiles;
+    if (splitk > nkb / 8) splitk = nkb / 8;
+    const size_t per = (size_t)M * N * sizeof(float);
+    while (splitk > 1 && per * splitk > splitk_ws_bytes) --splitk;
+    if (splitk < 1) splitk = 1;
+  }
+  a.kb_per_split = (nkb + splitk - 1) / splitk;
+  a.splitk = (nkb + a.kb_per_split - 1) / a.kb_per_split;
+  a.partial = static_cast<float*>(splitk_ws);
+  a.nmain = (a.kb_per_split + 11) / 12;  // <= 12 k-blocks (48 hi*hi MMAs) chained per accumulator
+  if (a.nmain < 1) a.nmain = 1;
+  if (a.nmain > NMAIN) a.nmain = NMAIN;
+  a.nsets = ((a.nmain + 1) * BN * 2 <= TMEM_COLS) ? 2 : 1;
+  const int nitems = ntiles * a.splitk;
+  dim3 grid(nitems < sms ? nitems : sms, 1, 1);
+  {
+    ProfScope prof(PROF_GEMM, stream);
+    gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(m_ahi, m_alo, m_bhi, m_blo, a);
+    B200_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  if (a.splitk > 1)
+    return launch_splitk_reduce(a.partial, a.splitk, M, N, C, c_rows, bias1, bias2, bias2_n, accumulate, stream);
   return B200RNN_OK;
+}
+
+int launch_gemm_tc(const GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (!gemm_tc_eligible(p, ws_bytes)) {
+    set_error("gemm_tc: problem not eligible for the tcgen05 path");
+    return B200RNN_ERR_UNSUPPORTED;
+  }
+  float* a_hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  float* a_lo = a_hi + (size_t)p.M * p.K;
+  float* b_hi = a_lo + (size_t)p.M * p.K;
+  float* b_lo = b_hi + (size_t)p.N * p.K;
+  int rc = tc_split(p.A, p.a_rows, p.M, p.K, a_hi, a_lo, stream);
+  if (rc) return rc;
+  rc = tc_split(p.B, p.b_rows, p.N, p.K, b_hi, b_lo, stream);
+  if (rc) return rc;
+  TcOperand A{a_hi, a_lo, p.K}, B{b_hi, b_lo, p.K};
+  return tc_gemm_presplit(A, B, p.M, p.N, p.K, p.C, p.c_rows, p.bias1, p.bias2, p.bias2_n, 0, nullptr, 0, stream);
 }
 
 }  // namespace b200rnn

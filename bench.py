@@ -253,22 +253,40 @@ def _time_module_train(kind: str, dev, iters: int = 20, warmup: int = 5) -> dict
     crit = torch.nn.CrossEntropyLoss()
 
     def step():
-        model.zero_grad(set_to_none=True)
-        x.grad = None
         loss = crit(model(x), y)
         loss.backward()
 
+    # warm-up (allocates .grad buffers), then capture forward+backward into one CUDA graph; grads accumulate in
+    # place across replays (zeroing them is an optimiser-side memset and is left out of "fwd+bwd")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    mode = "CUDA graph"
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        run = g.replay
+    except Exception as exc:
+        _log(f"{kind}: graph capture of fwd+bwd failed ({type(exc).__name__}); timing eager launches")
+        torch.cuda.synchronize()
+        run, mode = step, "eager"
     for _ in range(warmup):
-        step()
+        run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        step()
+        run()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    return {"fwd_bwd_ms_per_batch": ms, "sequences_per_s": 64 / ms * 1e3, "mode": "eager, dropout on, dx computed"}
+    return {"fwd_bwd_ms_per_batch": ms, "sequences_per_s": 64 / ms * 1e3,
+            "mode": mode + ", train mode (dropout on), dx computed, full model incl. loss"}
 
 
 def run_ours(args) -> None:
@@ -527,10 +545,18 @@ def run_ours(args) -> None:
                 "sample": f"{nst} train steps of B={B_PER_GPU} after 1 warm-up ({ms:.0f} ms/step) with the oracle port "
                           f"(oracle/ref_models.py on stock torch.nn CPU kernels, {cores} threads); with the reference's "
                           f"list->tensor conversion (fuse_net_whole.py:343) it is {v2:.1f} seq/s ({ms2:.0f} ms/step)"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    # Teardown: tearing an NCCL communicator down while captured graphs still hold its kernels can dead-lock
+    # (observed: 2-rank run hung in destroy_process_group after printing). Drop the graphs, sync, leave hard.
+    graphs.clear()
+    e2e_graphs.clear()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def _finetune_variant(dev, iters: int = 10, warmup: int = 3) -> dict:

@@ -25,6 +25,7 @@ SYMBOLS = (
     "b200rnn_launch_count",
     "b200rnn_workspace_bytes",
     "b200rnn_forward",
+    "b200rnn_forward_fused",
     "b200rnn_backward",
     "b200rnn_gemm_f32",
     "b200rnn_profile",
@@ -91,6 +92,8 @@ def load() -> ctypes.CDLL:
         c_uint64, c_uint64, c_void_p,                # seed, offset, rng_state
         c_void_p,                                    # stream
     ]
+    lib.b200rnn_forward_fused.restype = c_int
+    lib.b200rnn_forward_fused.argtypes = lib.b200rnn_forward.argtypes[:-1] + [c_void_p, c_void_p, c_float, c_void_p, c_void_p]
     lib.b200rnn_backward.restype = c_int
     lib.b200rnn_backward.argtypes = [
         POINTER(Desc), c_void_p, c_int64, c_int64,   # desc, x, strides

@@ -196,6 +196,46 @@ def rnn_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNNConfig
     return _RNNFunction.apply(x_tm, cfg, rng_state, grad_sink, *weights)
 
 
+@torch.no_grad()
+def rnn_forward_fused(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNNConfig,
+                      rng_state: Optional[torch.Tensor] = None, ln_weight: Optional[torch.Tensor] = None,
+                      ln_bias: Optional[torch.Tensor] = None, ln_eps: float = 1e-5, pool_sum: bool = False):
+    """No-grad forward with the shell fusions of ``b200rnn_forward_fused``: optional LayerNorm prologue on ``x``
+    and, with ``pool_sum``, the sum over time of the output instead of the sequence (``[B, D*H]``).
+
+    Mirrors ``x = ln(x); x, _ = gru(x); x = x.sum(dim=1)`` (fuse_net_whole.py:360-362). Returns ``(out, h_n[, c_n])``.
+    """
+    lib = _lib.load()
+    _require_cuda_f32(x, "input")
+    x_tm = _tm_view(x.transpose(0, 1) if cfg.batch_first else x)
+    T, B, _ = x_tm.shape
+    H, L, D = cfg.hidden_size, cfg.num_layers, cfg.num_dirs
+    dev = x.device
+    desc = _make_desc(cfg, B, T, False)
+    _, sbytes = _lib.workspace_bytes(desc)
+    scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+    if pool_sum:
+        out = torch.empty(B, D * H, dtype=torch.float32, device=dev)
+        y_ptr, ys_t, ys_b, pool_ptr = None, 0, 0, out.data_ptr()
+    elif cfg.batch_first:
+        out = torch.empty(B, T, D * H, dtype=torch.float32, device=dev)
+        y_ptr, ys_t, ys_b, pool_ptr = out.data_ptr(), D * H, T * D * H, None
+    else:
+        out = torch.empty(T, B, D * H, dtype=torch.float32, device=dev)
+        y_ptr, ys_t, ys_b, pool_ptr = out.data_ptr(), B * D * H, D * H, None
+    h_n = torch.empty(L * D, B, H, dtype=torch.float32, device=dev)
+    c_n = torch.empty(L * D, B, H, dtype=torch.float32, device=dev) if cfg.mode == _lib.LSTM else None
+    params = _lib.ptr_array([w.data_ptr() for w in weights])
+    rc = lib.b200rnn_forward_fused(
+        ctypes.byref(desc), x_tm.data_ptr(), x_tm.stride(0), x_tm.stride(1), params, y_ptr, ys_t, ys_b,
+        h_n.data_ptr(), c_n.data_ptr() if c_n is not None else None, None, scratch.data_ptr(), 0, 0,
+        rng_state.data_ptr() if rng_state is not None else None,
+        ln_weight.data_ptr() if ln_weight is not None else None, ln_bias.data_ptr() if ln_bias is not None else None,
+        float(ln_eps), pool_ptr, _stream_ptr())
+    _lib.check(rc, "b200rnn_forward_fused")
+    return (out, h_n) if c_n is None else (out, h_n, c_n)
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kcontig: bool = True, b_kcontig: bool = True,
          bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, accumulate: bool = False,
          use_splitk: bool = True) -> torch.Tensor:

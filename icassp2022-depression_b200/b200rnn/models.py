@@ -183,9 +183,9 @@ class fusion_net(nn.Module):  # noqa: N801  (reference class name)
             ctx = attention_pool(self.attention_layer, seq.permute(1, 0, 2), h_n.permute(1, 0, 2))
             text_feature = self.fc_out(ctx)
 
-            audio = batch.audio if self.regression else self.ln(batch.audio)
-            seq_a, _ = self.lstm_net_audio(audio)
-            audio_feature = self.fc_audio(seq_a.sum(dim=1))
+            # LayerNorm (classification flavour only) -> GRU -> sum over time, fused around the encoder
+            pooled = self.lstm_net_audio.forward_ln_sum(batch.audio, None if self.regression else self.ln)
+            audio_feature = self.fc_audio(pooled)
         return text_feature, audio_feature
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import RNNConfig, rnn_forward
+from .functional import RNNConfig, rnn_forward, rnn_forward_fused
 
 _TORCH_GRU = nn.GRU
 _TORCH_LSTM = nn.LSTM
@@ -140,6 +140,26 @@ class _B200RNNBase(nn.Module):
         if input.dim() != 3:
             raise NotImplementedError("b200rnn: unbatched 2-D input is not implemented")
         return rnn_forward(input, self._flat_weights, self._config(), self._rng_state, self._grad_sink)
+
+
+    def forward_ln_sum(self, input: torch.Tensor, ln: Optional[nn.LayerNorm] = None) -> torch.Tensor:
+        """``self(ln(input))[0].sum(dim=time)`` — the audio branch of fuse_net_whole.py:360-362 / fuse_net.py:338-339.
+
+        Without autograd (the reference runs it under ``torch.no_grad()``, fuse_net_whole.py:337) and for widths the
+        tensor-core projection takes, LayerNorm is folded into the layer-0 operand preparation and the time sum into
+        the last layer's step loop, so the normalised input and the [B,T,H] output never touch HBM. Otherwise the same
+        value is computed unfused.
+        """
+        need_grad = torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters()))
+        fusable = (not need_grad and input.is_cuda and input.dim() == 3 and self.input_size % 128 == 0 and
+                   self.input_size <= 1024 and (ln is None or (ln.elementwise_affine and ln.bias is not None)))
+        if fusable:
+            out = rnn_forward_fused(input, self._flat_weights, self._config(), self._rng_state,
+                                    ln.weight if ln is not None else None, ln.bias if ln is not None else None,
+                                    ln.eps if ln is not None else 1e-5, pool_sum=True)
+            return out[0]
+        seq = self(ln(input) if ln is not None else input)[0]
+        return seq.sum(dim=1 if self.batch_first else 0)
 
 
 class GRU(_B200RNNBase):

@@ -229,18 +229,27 @@ B200RNN_API int b200rnn_workspace_bytes(const b200rnn_desc* desc, size_t* reserv
   return B200RNN_OK;
 }
 
-B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_t xs_t, int64_t xs_b,
-                                const float* const* params, float* y, int64_t ys_t, int64_t ys_b, float* h_n,
-                                float* c_n, void* reserve, void* scratch, uint64_t seed, uint64_t offset,
-                                uint64_t* rng_state, void* stream_) {
+B200RNN_API int b200rnn_forward_fused(const b200rnn_desc* desc, const float* x, int64_t xs_t, int64_t xs_b,
+                                      const float* const* params, float* y, int64_t ys_t, int64_t ys_b, float* h_n,
+                                      float* c_n, void* reserve, void* scratch, uint64_t seed, uint64_t offset,
+                                      uint64_t* rng_state, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                                      float* y_pool, void* stream_) {
   Dims d;
   int rc = check_desc(desc, &d);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   if (d.B == 0 || d.T == 0) return B200RNN_OK;
   const bool save = (desc->flags & B200RNN_FLAG_SAVE_FOR_BACKWARD) != 0;
-  if (!x || !params || !y || !h_n || (d.mode == B200RNN_LSTM && !c_n)) {
+  if (!x || !params || (!y && !y_pool) || !h_n || (d.mode == B200RNN_LSTM && !c_n)) {
     set_error("forward: null pointer argument");
+    return B200RNN_ERR_INVALID;
+  }
+  if (!y && save) {
+    set_error("forward: the full output is needed by backward; pooled-only output requires a no-grad forward");
+    return B200RNN_ERR_INVALID;
+  }
+  if ((ln_gamma == nullptr) != (ln_beta == nullptr)) {
+    set_error("forward: LayerNorm prologue needs both gamma and beta");
     return B200RNN_ERR_INVALID;
   }
   if (save && !reserve) {
@@ -269,6 +278,8 @@ B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_
     if (rc) return rc;
   }
 
+  const bool tc = tc_available();
+  bool a_ready = false;  // the next layer's A operand (hi/lo) was already produced by this layer's dropout pass
   for (int l = 0; l < d.L; ++l) {
     const int Il = l == 0 ? d.I : (int)d.DH;
     // ---- layer input ---------------------------------------------------------------------------
@@ -284,6 +295,22 @@ B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_
         in = S + sl.f_y[(l - 1) & 1];
       in_rows = simple_rows((long long)d.DH);
     }
+    // ---- A operand of the tensor-core input projection, prepared once per layer (shared by the directions)
+    const bool tc_layer = tc && (Il % 32 == 0) && (d.GH % 128 == 0);
+    void* tc_ws = S + sl.f_tc;
+    if (tc_layer) {
+      float* a_hi = tc_a_hi(tc_ws);
+      float* a_lo = tc_a_lo(tc_ws, (int)d.TB, Il);
+      if (l == 0 && ln_gamma)
+        rc = tc_layernorm_split(in, in_rows, (int)d.TB, Il, ln_gamma, ln_beta, ln_eps, a_hi, a_lo, st);
+      else if (!a_ready)
+        rc = tc_split(in, in_rows, (int)d.TB, Il, a_hi, a_lo, st);
+      if (rc) return rc;
+    } else if (l == 0 && ln_gamma) {
+      set_error("forward: the fused LayerNorm prologue needs the tensor-core input projection (input_size %% 32 == 0)");
+      return B200RNN_ERR_UNSUPPORTED;
+    }
+    a_ready = false;
     RecFwdParams rp;
     memset(&rp, 0, sizeof(rp));
     rp.mode = d.mode; rp.B = d.B; rp.T = d.T; rp.H = d.H; rp.D = d.D;
@@ -309,8 +336,11 @@ B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_
       g.M = (int)d.TB; g.N = (int)d.GH; g.K = Il;
       g.bias1 = b_ih; g.bias2 = b_hh;
       g.bias2_n = d.mode == B200RNN_GRU ? 2 * d.H : 4 * d.H;
-      g.tc_ws = S + sl.f_tc;
-      g.tc_ws_bytes = sl.f_tc_bytes;
+      if (tc_layer) {
+        g.tc_ws = tc_ws;
+        g.tc_ws_bytes = sl.f_tc_bytes;
+        g.tc_a_presplit = 1;
+      }
       rc = launch_gemm(g, nullptr, 0, st);
       if (rc) return rc;
       rp.w_hh[k] = w_hh;
@@ -321,6 +351,7 @@ B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_
     float* ylay = nullptr;
     if (l == d.L - 1) {
       rp.y = y; rp.y_st = ys_t; rp.y_sb = ys_b;
+      rp.y_pool = y_pool;
     } else {
       ylay = save ? R + rl.ylayer[l] : S + sl.f_y[l & 1];
       rp.y = ylay;
@@ -332,11 +363,26 @@ B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_
     rc = launch_rec_fwd(rp, st);
     if (rc) return rc;
     if (drop && l + 1 < d.L) {  // K7; keeps the raw output when it is needed by backward, else in place
-      rc = launch_dropout(ylay, save ? R + rl.ydrop[l] : ylay, d.TB * d.DH, d.p, hdr, (uint32_t)l, st);
+      float* dropped = save ? R + rl.ydrop[l] : ylay;
+      if (tc) {  // also emit the hi/lo split the next layer's tensor-core GEMM consumes (one pass instead of two)
+        rc = launch_dropout_split(ylay, dropped, tc_a_hi(tc_ws), tc_a_lo(tc_ws, (int)d.TB, (int)d.DH), d.TB * d.DH, d.p, hdr,
+                                  (uint32_t)l, st);
+        a_ready = true;
+      } else {
+        rc = launch_dropout(ylay, dropped, d.TB * d.DH, d.p, hdr, (uint32_t)l, st);
+      }
       if (rc) return rc;
     }
   }
   return B200RNN_OK;
+}
+
+B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_t xs_t, int64_t xs_b,
+                                const float* const* params, float* y, int64_t ys_t, int64_t ys_b, float* h_n,
+                                float* c_n, void* reserve, void* scratch, uint64_t seed, uint64_t offset,
+                                uint64_t* rng_state, void* stream_) {
+  return b200rnn_forward_fused(desc, x, xs_t, xs_b, params, y, ys_t, ys_b, h_n, c_n, reserve, scratch, seed, offset,
+                               rng_state, nullptr, nullptr, 0.f, nullptr, stream_);
 }
 
 B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64_t xs_t, int64_t xs_b,

@@ -22,7 +22,15 @@ struct GemmParams {
   // optional workspace for the tcgen05 3xTF32 path (gemm_tc.cu); NULL => fp32 FFMA path
   void* tc_ws;
   size_t tc_ws_bytes;
+  int tc_a_presplit;  // the A operand's hi/lo halves already sit at tc_ws (see tc_a_hi / tc_a_lo)
 };
+
+// where launch_gemm_tc expects / puts the split A operand inside its workspace
+float* tc_a_hi(void* ws);
+float* tc_a_lo(void* ws, int M, int K);
+// LayerNorm over the last dimension fused with the TF32 split: hi/lo <- split(LN(src row) * gamma + beta)
+int tc_layernorm_split(const float* src, const RowMap& rows, int R, int Cc, const float* gamma, const float* beta,
+                       float eps, float* hi, float* lo, cudaStream_t stream);
 
 // tcgen05 3xTF32 path: C = A[M,K] * B[N,K]^T + biases (both operands k-contiguous, K % 32 == 0, N % 128 == 0)
 size_t gemm_tc_scratch_bytes(int M, int N, int K);

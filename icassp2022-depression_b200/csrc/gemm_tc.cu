@@ -314,6 +314,56 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, RowMap rows, in
   }
 }
 
+// LayerNorm(row) * gamma + beta, then the TF32 split — the prologue of audio_gru_whole.py:104 / fuse_net_whole.py:360
+// folded into the operand preparation of K1. One warp per row; Cc % 128 == 0, Cc <= 1024.
+template <int NV>  // float4 per lane
+__global__ void layernorm_split_kernel(const float* __restrict__ src, RowMap rows, int R, int Cc,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                       float* __restrict__ hi, float* __restrict__ lo) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += gridDim.x * wpb) {
+    const float* p = src + rows.off(r);
+    float4 x[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      x[i] = __ldg(reinterpret_cast<const float4*>(p + i * 128 + lane * 4));
+      s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)Cc;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+      v += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v / (float)Cc + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int k = i * 128 + lane * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + k));
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + k));
+      float y[4] = {(x[i].x - mean) * rstd * g.x + bt.x, (x[i].y - mean) * rstd * g.y + bt.y,
+                    (x[i].z - mean) * rstd * g.z + bt.z, (x[i].w - mean) * rstd * g.w + bt.w};
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(y[e]));
+        h[e] = __uint_as_float(t);
+        l[e] = y[e] - h[e];
+      }
+      *reinterpret_cast<float4*>(hi + (size_t)r * Cc + k) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(lo + (size_t)r * Cc + k) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
 // Transposing variant: src [R rows (RowMap), Cc columns]  ->  hiT / loT [Cc][ldT] (element (c, r) at c*ldT + r).
 // Turns the "MN-major" operands of the wgrad GEMMs (dG^T, X^T, H_prev^T) into the K-major form the kernel takes.
 __global__ void split_tf32_transpose_kernel(const float* __restrict__ src, RowMap rows, int R, int Cc,
@@ -426,6 +476,35 @@ int tc_split_transpose(const float* src, const RowMap& rows, int R, int Cc, floa
 
 bool tc_available() { return !tc_disabled() && get_encoder() != nullptr; }
 
+float* tc_a_hi(void* ws) { return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255); }
+float* tc_a_lo(void* ws, int M, int K) { return tc_a_hi(ws) + (size_t)M * K; }
+
+int tc_layernorm_split(const float* src, const RowMap& rows, int R, int Cc, const float* gamma, const float* beta,
+                       float eps, float* hi, float* lo, cudaStream_t stream) {
+  const bool vec = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && rows.s_outer % 4 == 0 && rows.s_inner % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15u) == 0;
+  if (!vec || Cc % 128 != 0 || Cc > 1024 || Cc < 128) {
+    set_error("layernorm_split: needs 16-byte aligned rows and a feature width in {128,...,1024} multiple of 128");
+    return B200RNN_ERR_UNSUPPORTED;
+  }
+  int blocks = (R + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope prof(PROF_MISC, stream);
+  switch (Cc / 128) {
+    case 1: layernorm_split_kernel<1><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
+    case 2: layernorm_split_kernel<2><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
+    case 3: layernorm_split_kernel<3><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
+    case 4: layernorm_split_kernel<4><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
+    case 5: layernorm_split_kernel<5><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
+    case 6: layernorm_split_kernel<6><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
+    case 7: layernorm_split_kernel<7><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
+    default: layernorm_split_kernel<8><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
+  }
+  B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return B200RNN_OK;
+}
+
 // C[M,N] (+)= A[M,K] * B[N,K]^T (+ biases), operands already split into hi/lo K-major matrices.
 int tc_gemm_presplit(const TcOperand& A, const TcOperand& B, int M, int N, int K, float* C, const RowMap& c_rows,
                      const float* bias1, const float* bias2, int bias2_n, int accumulate, void* splitk_ws,
@@ -501,11 +580,12 @@ int launch_gemm_tc(const GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t 
     set_error("gemm_tc: problem not eligible for the tcgen05 path");
     return B200RNN_ERR_UNSUPPORTED;
   }
-  float* a_hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  float* a_lo = a_hi + (size_t)p.M * p.K;
+  float* a_hi = tc_a_hi(ws);
+  float* a_lo = tc_a_lo(ws, p.M, p.K);
   float* b_hi = a_lo + (size_t)p.M * p.K;
   float* b_lo = b_hi + (size_t)p.N * p.K;
-  int rc = tc_split(p.A, p.a_rows, p.M, p.K, a_hi, a_lo, stream);
+  int rc = B200RNN_OK;
+  if (!p.tc_a_presplit) rc = tc_split(p.A, p.a_rows, p.M, p.K, a_hi, a_lo, stream);
   if (rc) return rc;
   rc = tc_split(p.B, p.b_rows, p.N, p.K, b_hi, b_lo, stream);
   if (rc) return rc;

@@ -15,6 +15,11 @@ int launch_rng_setup(uint64_t* hdr, uint64_t seed, uint64_t offset, uint64_t* st
 int launch_dropout(const float* in, float* out, size_t n, float p, const uint64_t* hdr, uint32_t stream_id,
                    cudaStream_t stream);
 
+// Same, and additionally emits the TF32 hi/lo split of the dropped values (operand of the next layer's K1 GEMM),
+// saving a separate pass over the layer output. n must be a multiple of 4, all pointers 16-byte aligned.
+int launch_dropout_split(const float* in, float* out, float* hi, float* lo, size_t n, float p, const uint64_t* hdr,
+                         uint32_t stream_id, cudaStream_t stream);
+
 // dst[c][r] = src[r][c]   (src [rows, cols] row-major)
 int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t stream);
 

@@ -12,8 +12,9 @@ struct RecFwdParams {
   const float* b_hh[2];      // per direction [G*H]  (GRU: only the n third is read; r,z are pre-folded)
   float* gates[2];           // per direction [T,B,G*H]; in: x-projection + folded biases; out: activated gates
   float* extra[2];           // per direction [T,B,H]; GRU: W_hn h + b_hn ; LSTM: c_t   (training only)
-  float* y;                  // layer output, element (t,b,d*H+j) at t*y_st + b*y_sb + d*H + j
+  float* y;                  // layer output, element (t,b,d*H+j) at t*y_st + b*y_sb + d*H + j (NULL: not written)
   long long y_st, y_sb;
+  float* y_pool;             // optional [B, D*H]: sum over t of the layer output (fused pooling epilogue)
   float* h_n;                // [D,B,H] of this layer
   float* c_n;                // [D,B,H] of this layer (LSTM) or NULL
   long long* trace;          // debug: per-step phase timestamps of CTA 0 / warp 0 (NULL = off), [T][8]

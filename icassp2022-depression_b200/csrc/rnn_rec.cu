@@ -55,7 +55,7 @@ struct RecCfg {
   static constexpr size_t BWD_SMEM = W_BYTES + (size_t)2 * BS * GH * sizeof(float) + BAR_BYTES;
   static_assert(NBAR * 8 <= (int)BAR_BYTES, "barrier block too small");
   static_assert(ROT ? (HS % CW == 0) : (CW % HS == 0), "chunks must tile the per-CTA slices");
-  static_assert(RG == 0 || RG == 1, "at most one register-resident gate block");
+  static_assert(RG >= 0 && RG <= 2, "at most two register-resident gate blocks");
   static_assert(HS * C == H && NW * UPW == HS && NW >= 1, "bad split");
   static_assert(UPW % 4 == 0, "the exchange packs 4 units per 16-byte store");
   static_assert(NT <= 1024, "too many threads");
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
   }
   for (int i = tid; i < 2 * BS * H; i += NT) h_s[i] = 0.f;  // h_0 = 0 (rnn.py:1432-1440)
   const int rot = Cfg::ROT ? (int)rank * CPS : 0;
-  float wreg[1][UPL][H / KL];
+  float wreg[RG > 0 ? RG : 1][UPL][H / KL];
   load_resident<RG, KL, UPL, BS, H>(w_hh, H, (long long)NSM * H + j0 + w * UPW, rot, lane, wreg);
   ptx::mbar_wait(&bars[0], 0);
   __syncthreads();
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
   float* extra = p.extra[dir];
   const float bhn = (MODE == B200RNN_GRU) ? p.b_hh[dir][2 * H + j] : 0.f;
 
-  float h_prev = 0.f, c_prev = 0.f;
+  float h_prev = 0.f, c_prev = 0.f, h_sum = 0.f;
   float gi[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) gi[g] = 0.f;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     long long* trow = p.trace + (size_t)step * 8;
     if (tr) trow[0] = clock64();
 
-    constexpr bool PACK2 = (MODE == B200RNN_GRU);  // FFMA2 pays off only where the register budget allows it
+    constexpr bool PACK2 = (MODE == B200RNN_GRU) && RG < 2;  // FFMA2 only where the register budget allows it
     float2 acc2[PACK2 ? G : 1][UPL][BS];
     float acc[G][UPL][BS];
 #pragma unroll
@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
       s0 = ig; s1 = fg; s2 = gg; s3 = og; sx = cnew;
     }
     h_prev = hnew;
+    h_sum += hnew;
     if (tr) trow[4] = clock64() + (long long)(hnew == 12345.678f);
 
     if (step + 1 < T)
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
 
     // off the critical path: global stores of this step, prefetch of the next step's x-projection
     if (valid) {
-      p.y[(long long)t * p.y_st + (long long)b * p.y_sb + dir * H + j] = hnew;
+      if (p.y) p.y[(long long)t * p.y_st + (long long)b * p.y_sb + dir * H + j] = hnew;
       if (p.training) {
         float* gp = gates + ((size_t)t * B + b) * GH + j;
         gp[0] = s0;
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
       }
       if (step == T - 1) {
         p.h_n[((size_t)dir * B + b) * H + j] = hnew;
+        if (p.y_pool) p.y_pool[(size_t)b * p.D * H + dir * H + j] = h_sum;
         if (MODE == B200RNN_LSTM && p.c_n) p.c_n[((size_t)dir * B + b) * H + j] = c_prev;
       }
       if (step + 1 < T) {
@@ -293,6 +295,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     rec_bwd_kernel(const RecBwdParams p, const int nslices) {
   using Cfg = RecCfg<MODE, H, C, BS, KL, UPL, RG>;
   using LM = LaneMap<KL, UPL, BS>;
+  static_assert(RG <= 1, "the backward kernel keeps at most one gate block in registers");
   constexpr int G = Cfg::G, GH = Cfg::GH, HS = Cfg::HS, NT = Cfg::NT, UPW = Cfg::UPW, NSM = Cfg::NSM;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* W_s = reinterpret_cast<float*>(smem_raw);   // [NSM][HS][H] transposed gate blocks
@@ -616,6 +619,8 @@ int launch_rec_fwd(const RecFwdParams& p, cudaStream_t s) {
       return rc;
     } else if (variant == 4) {  // 128-thread CTAs, two per SM: two independent recurrences overlap their latency
       if (try_fwd<B200RNN_GRU, 256, 8, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    } else if (variant == 5) {  // two gate blocks in registers: halves the shared-memory weight traffic per step
+      if (try_fwd<B200RNN_GRU, 256, 4, 4, 16, 4, 2>(p, s, false, &rc)) return rc;
     } else {  // default: measured fastest on B200 (232 us for B=128, T=120)
       if (try_fwd<B200RNN_GRU, 256, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
     }

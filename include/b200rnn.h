@@ -118,6 +118,22 @@ B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_
                                 void* stream /* cudaStream_t */);
 
 /*
+ * Forward with the model-shell fusions around the encoder, used by the audio branch
+ * `x = self.ln(x); x, _ = self.lstm_net_audio(x); x = x.sum(dim=1)` of fuse_net_whole.py:360-362:
+ *   ln_gamma/ln_beta/ln_eps : LayerNorm over the feature dimension applied to x on the fly (folded into the operand
+ *                             preparation of the layer-0 input projection); NULL = no LayerNorm
+ *   y_pool                  : optional [B, D*H] = sum over time of the top layer's output; with y == NULL the
+ *                             [T,B,D*H] output is never written (only allowed without B200RNN_FLAG_SAVE_FOR_BACKWARD)
+ * Everything else as b200rnn_forward (which is this call with the four extra arguments zero).
+ */
+B200RNN_API int b200rnn_forward_fused(const b200rnn_desc* desc, const float* x, int64_t x_stride_t,
+                                      int64_t x_stride_b, const float* const* params, float* y, int64_t y_stride_t,
+                                      int64_t y_stride_b, float* h_n, float* c_n, void* reserve, void* scratch,
+                                      uint64_t dropout_seed, uint64_t dropout_offset, uint64_t* rng_state,
+                                      const float* ln_gamma, const float* ln_beta, float ln_eps, float* y_pool,
+                                      void* stream /* cudaStream_t */);
+
+/*
  * Backward pass (BPTT): what autograd runs for loss.backward() through nn.GRU / nn.LSTM
  * (audio_gru_whole.py:190, text_bilstm_whole.py:182). `desc` must equal the forward's.
  *

@@ -145,3 +145,43 @@ def test_data_parallel_shards_reproduce_full_batch_gradient():
         k += n
         assert (g - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-9
     assert k == full.numel()
+
+
+@pytest.mark.parametrize("use_ln,train_mode", [(True, False), (False, False), (True, True)])
+def test_fused_ln_gru_sum_matches_unfused(use_ln, train_mode):
+    """b200rnn_forward_fused (LayerNorm prologue + time-sum epilogue) == ln -> GRU -> sum(dim=1)."""
+    import b200rnn
+
+    torch.manual_seed(3)
+    gru = b200rnn.GRU(256, 256, num_layers=2, dropout=0.0, batch_first=True).to(DEV)
+    ln = torch.nn.LayerNorm(256).to(DEV)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.2, 0.2)
+    gru.train(train_mode)
+    x = torch.randn(9, 14, 256, device=DEV) * 3 + 1
+    with torch.no_grad():
+        fused = gru.forward_ln_sum(x, ln if use_ln else None)
+        ref = gru(ln(x) if use_ln else x)[0].sum(dim=1)
+    assert fused.shape == ref.shape == (9, 256)
+    assert (fused - ref).abs().max().item() <= 2e-5   # sum of 14 outputs, each within 1e-6
+    # CPU oracle of the same expression
+    cpu = torch.nn.GRU(256, 256, num_layers=2, batch_first=True)
+    cpu.load_state_dict(gru.state_dict())
+    ln_cpu = torch.nn.LayerNorm(256)
+    ln_cpu.load_state_dict(ln.state_dict())
+    with torch.no_grad():
+        xc = x.cpu()
+        oracle = cpu(ln_cpu(xc) if use_ln else xc)[0].sum(dim=1)
+    assert (fused.cpu() - oracle).abs().max().item() <= 5e-5
+
+
+def test_fused_path_falls_back_under_autograd():
+    import b200rnn
+
+    gru = b200rnn.GRU(256, 256, num_layers=1, batch_first=True).to(DEV)
+    ln = torch.nn.LayerNorm(256).to(DEV)
+    x = torch.randn(3, 4, 256, device=DEV, requires_grad=True)
+    out = gru.forward_ln_sum(x, ln)
+    out.sum().backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all()

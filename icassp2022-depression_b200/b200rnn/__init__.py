@@ -11,9 +11,10 @@ from .functional import RNNConfig, gemm, rnn_forward
 from .staging import FuseBatch, PinnedStager, stage_fuse_batch
 from .dp import GradBucket, broadcast_parameters, shard_batch
 from .models import AudioBiLSTM, MyLoss, TextBiLSTM, attention_pool, fusion_net
+from .fused_head import FusedFuseStep
 
 __all__ = [
     "GRU", "LSTM", "install", "uninstall", "from_torch", "rnn_forward", "gemm", "RNNConfig", "B200RNNError",
     "AudioBiLSTM", "TextBiLSTM", "fusion_net", "MyLoss", "attention_pool", "FuseBatch", "PinnedStager",
-    "stage_fuse_batch", "GradBucket", "broadcast_parameters", "shard_batch",
+    "stage_fuse_batch", "GradBucket", "broadcast_parameters", "shard_batch", "FusedFuseStep",
 ]

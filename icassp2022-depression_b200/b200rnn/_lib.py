@@ -28,6 +28,11 @@ SYMBOLS = (
     "b200rnn_forward_fused",
     "b200rnn_backward",
     "b200rnn_gemm_f32",
+    "b200rnn_attention_pool",
+    "b200rnn_mlp_dropout",
+    "b200rnn_rng_next",
+    "b200rnn_fuse_loss_grad",
+    "b200rnn_adam",
     "b200rnn_profile",
     "b200rnn_profile_read",
 )
@@ -111,6 +116,20 @@ def load() -> ctypes.CDLL:
         c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p,
         c_int, c_void_p, c_size_t, c_void_p,
     ]
+    lib.b200rnn_attention_pool.restype = c_int
+    lib.b200rnn_attention_pool.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                           c_void_p, c_void_p, c_void_p]
+    lib.b200rnn_mlp_dropout.restype = c_int
+    lib.b200rnn_mlp_dropout.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
+                                        c_uint32, c_void_p]
+    lib.b200rnn_rng_next.restype = c_int
+    lib.b200rnn_rng_next.argtypes = [c_void_p, c_void_p, c_uint64, c_void_p]
+    lib.b200rnn_fuse_loss_grad.restype = c_int
+    lib.b200rnn_fuse_loss_grad.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                           c_void_p, c_void_p, c_void_p]
+    lib.b200rnn_adam.restype = c_int
+    lib.b200rnn_adam.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
+                                 c_float, c_void_p]
     lib.b200rnn_profile.restype = c_int
     lib.b200rnn_profile.argtypes = [c_int]
     lib.b200rnn_profile_read.restype = c_int

@@ -1,0 +1,317 @@
+// head_kernels.cu — the small dense shells on either side of the encoders inside the fuse step, fused into a
+// handful of kernels (SURVEY.md 8f rank 1 "attention pooling as one small kernel", rank 3 "fused optimiser + loss").
+// They replace ~45 tiny framework launches per step of fuse_net_whole.py:336-366, 445-456:
+//   attention_pool_kernel : attention_net_with_w (text_bilstm_whole.py:74-99 / fuse_net_whole.py:310-334)
+//   mlp_dropout_kernel    : Dropout -> Linear -> ReLU -> Dropout   (fc_out / fc_audio of fusion_net, :270-275, :288-293)
+//   fuse_loss_grad_kernel : Softmax(fc_final(concat)), MyLoss two-head CE, and d loss / d fc_final.0.weight (:368-395)
+//   adam_kernel           : torch.optim.Adam step (no weight decay / amsgrad) over a flat parameter range (:416, :456)
+// All are latency-bound dwarfs (a few KB..MB); the point is launch count, not bandwidth.
+#include "common.cuh"
+#include "misc_kernels.cuh"
+
+namespace b200rnn {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// keep-mask of element `idx` of dropout stream `stream_id` (same Philox layout as dropout_kernel: 4 per call)
+__device__ __forceinline__ float keep_scale(const uint64_t* hdr, uint32_t stream_id, size_t idx, uint32_t thr,
+                                            float scale) {
+  Philox4 r = philox4x32_10(hdr[0], hdr[1] + (idx >> 2), (uint64_t)stream_id);
+  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+  return rr[idx & 3] >= thr ? scale : 0.f;
+}
+
+// ---- attention pooling: one CTA per batch row ------------------------------------------------------------
+//   seq   : [T,B,2H] addressed t*s_t + b*s_b + c   (fwd | rev halves)
+//   h_n   : [NS,B,H]  final hidden states (all layers / directions), summed
+//   ctx[b] = sum_t softmax_t( ReLU(W_a hsum + b_a) . tanh(h_t) ) * h_t,   h_t = seq[t,b,:H] + seq[t,b,H:]
+__global__ void attention_pool_kernel(const float* __restrict__ seq, long long s_t, long long s_b,
+                                      const float* __restrict__ h_n, int NS, int B, int T, int H,
+                                      const float* __restrict__ w_a, const float* __restrict__ b_a,
+                                      float* __restrict__ ctx) {
+  extern __shared__ float sm[];
+  float* hsum = sm;          // [H]
+  float* q = sm + H;         // [H]
+  float* score = sm + 2 * H; // [T]
+  __shared__ float red[2];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+
+  for (int j = tid; j < H; j += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < NS; ++k) s += h_n[((size_t)k * B + b) * H + j];
+    hsum[j] = s;
+  }
+  __syncthreads();
+  for (int i = warp; i < H; i += nw) {  // q = ReLU(W_a hsum + b_a), one warp per output row
+    float s = 0.f;
+    for (int j = lane; j < H; j += 32) s += w_a[(size_t)i * H + j] * hsum[j];
+    s = warp_sum(s);
+    if (lane == 0) q[i] = fmaxf(s + b_a[i], 0.f);
+  }
+  __syncthreads();
+  const float* row0 = seq + (long long)b * s_b;
+  for (int t = warp; t < T; t += nw) {  // scores, one warp per time step
+    const float* r = row0 + (long long)t * s_t;
+    float s = 0.f;
+    for (int j = lane; j < H; j += 32) s += q[j] * tanhf(r[j] + r[H + j]);
+    s = warp_sum(s);
+    if (lane == 0) score[t] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {  // softmax over T
+    float m = -INFINITY;
+    for (int t = lane; t < T; t += 32) m = fmaxf(m, score[t]);
+    m = warp_max(m);
+    float z = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const float e = expf(score[t] - m);
+      score[t] = e;
+      z += e;
+    }
+    z = warp_sum(z);
+    if (lane == 0) red[0] = 1.f / z;
+  }
+  __syncthreads();
+  const float inv = red[0];
+  for (int j = tid; j < H; j += blockDim.x) {
+    float a = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float* r = row0 + (long long)t * s_t;
+      a += score[t] * (r[j] + r[H + j]);
+    }
+    ctx[(size_t)b * H + j] = a * inv;
+  }
+}
+
+// ---- out = D2(ReLU(W D1(x) + bias)), one CTA per row ------------------------------------------------------
+__global__ void mlp_dropout_kernel(const float* __restrict__ x, int n, const float* __restrict__ W,
+                                   const float* __restrict__ bias, float* __restrict__ out, int training, float p,
+                                   const uint64_t* __restrict__ hdr, uint32_t stream_id) {
+  extern __shared__ float xs[];  // [n]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const bool drop = training && p > 0.f;
+  const uint32_t thr = (uint32_t)fminf(p * 4294967296.0f, 4294967295.0f);
+  const float scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  for (int j = tid; j < n; j += blockDim.x) {
+    float v = x[(size_t)b * n + j];
+    if (drop) v *= keep_scale(hdr, stream_id, (size_t)b * n + j, thr, scale);
+    xs[j] = v;
+  }
+  __syncthreads();
+  for (int i = warp; i < n; i += nw) {
+    float s = 0.f;
+    for (int j = lane; j < n; j += 32) s += W[(size_t)i * n + j] * xs[j];
+    s = warp_sum(s);
+    if (lane == 0) {
+      float v = fmaxf(s + bias[i], 0.f);
+      if (drop) v *= keep_scale(hdr, stream_id + 1, (size_t)b * n + i, thr, scale);
+      out[(size_t)b * n + i] = v;
+    }
+  }
+}
+
+// ---- two-head cross entropy on the halves of fc_final.0.weight, its gradient, and the fused softmax output ------
+//   W [2, Ht+Ha];  loss = CE(tf W[:, :Ht]^T, y) + CE(af W[:, Ht:]^T, y)  (mean over B)
+//   dW (+)= d loss / dW ;  probs = softmax(cat(tf,af) W^T)
+constexpr int LOSS_THREADS = 256;
+constexpr int LOSS_MAXF = 1024;  // Ht + Ha
+__global__ void __launch_bounds__(LOSS_THREADS)
+    fuse_loss_grad_kernel(const float* __restrict__ tf, int Ht, const float* __restrict__ af, int Ha,
+                          const long long* __restrict__ labels, int B, const float* __restrict__ W,
+                          float* __restrict__ dW, int accumulate, float* __restrict__ loss_out,
+                          float* __restrict__ probs) {
+  extern __shared__ float dyn[];  // [nw][2][F] per-warp gradient partials, then [nw] loss partials
+  const int F = Ht + Ha;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = LOSS_THREADS / 32;
+  float* gpart = dyn + (size_t)warp * 2 * F;
+  float* lpart = dyn + (size_t)nw * 2 * F;
+  for (int i = lane; i < 2 * F; i += 32) gpart[i] = 0.f;
+  __syncwarp();
+  float lsum = 0.f;
+  const float invB = 1.f / (float)B;
+  for (int b = warp; b < B; b += nw) {
+    const float* t = tf + (size_t)b * Ht;
+    const float* a = af + (size_t)b * Ha;
+    float pt0 = 0.f, pt1 = 0.f, pa0 = 0.f, pa1 = 0.f;
+    for (int j = lane; j < Ht; j += 32) {
+      const float v = t[j];
+      pt0 += v * W[j];
+      pt1 += v * W[F + j];
+    }
+    for (int j = lane; j < Ha; j += 32) {
+      const float v = a[j];
+      pa0 += v * W[Ht + j];
+      pa1 += v * W[F + Ht + j];
+    }
+    pt0 = warp_sum(pt0); pt1 = warp_sum(pt1); pa0 = warp_sum(pa0); pa1 = warp_sum(pa1);
+    const int y = (int)labels[b];
+    // head: text
+    float m = fmaxf(pt0, pt1), e0 = expf(pt0 - m), e1 = expf(pt1 - m), z = e0 + e1;
+    const float st0 = e0 / z, st1 = e1 / z;
+    lsum += (m + logf(z)) - (y == 0 ? pt0 : pt1);
+    // head: audio
+    m = fmaxf(pa0, pa1); e0 = expf(pa0 - m); e1 = expf(pa1 - m); z = e0 + e1;
+    const float sa0 = e0 / z, sa1 = e1 / z;
+    lsum += (m + logf(z)) - (y == 0 ? pa0 : pa1);
+    const float dt0 = (st0 - (y == 0 ? 1.f : 0.f)) * invB, dt1 = (st1 - (y == 1 ? 1.f : 0.f)) * invB;
+    const float da0 = (sa0 - (y == 0 ? 1.f : 0.f)) * invB, da1 = (sa1 - (y == 1 ? 1.f : 0.f)) * invB;
+    for (int j = lane; j < Ht; j += 32) {
+      const float v = t[j];
+      gpart[j] += dt0 * v;
+      gpart[F + j] += dt1 * v;
+    }
+    for (int j = lane; j < Ha; j += 32) {
+      const float v = a[j];
+      gpart[Ht + j] += da0 * v;
+      gpart[F + Ht + j] += da1 * v;
+    }
+    if (probs && lane == 0) {  // Softmax(fc_final(concat)) — used by the reference for accuracy only
+      const float l0 = pt0 + pa0, l1 = pt1 + pa1, mm = fmaxf(l0, l1);
+      const float x0 = expf(l0 - mm), x1 = expf(l1 - mm);
+      probs[(size_t)b * 2 + 0] = x0 / (x0 + x1);
+      probs[(size_t)b * 2 + 1] = x1 / (x0 + x1);
+    }
+  }
+  if (lane == 0) lpart[warp] = lsum;
+  __syncthreads();
+  for (int i = tid; i < 2 * F; i += LOSS_THREADS) {  // fixed summation order over warps => deterministic
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += dyn[(size_t)w * 2 * F + i];
+    dW[i] = accumulate ? dW[i] + s : s;
+  }
+  if (tid == 0) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += lpart[w];
+    *loss_out = s * invB;
+  }
+}
+
+// ---- Adam (torch.optim.Adam defaults: no weight decay, no amsgrad), step counter on the device ------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, const float* __restrict__ step, size_t n, float lr, float b1,
+                            float b2, float eps) {
+  const float t = *step + 1.f;  // the increment itself is done by adam_step_kernel after this launch
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+__global__ void adam_step_kernel(float* step) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *step += 1.f;
+}
+
+}  // namespace
+}  // namespace b200rnn
+
+using namespace b200rnn;
+
+extern "C" {
+
+B200RNN_API int b200rnn_attention_pool(const float* seq, int64_t s_t, int64_t s_b, const float* h_n, int n_states,
+                                       int B, int T, int H, const float* w_a, const float* b_a, float* ctx,
+                                       void* stream_) {
+  if (!seq || !h_n || !w_a || !b_a || !ctx || B < 0 || T < 1 || H < 1 || n_states < 1) {
+    set_error("attention_pool: bad argument");
+    return B200RNN_ERR_INVALID;
+  }
+  if (B == 0) return B200RNN_OK;
+  const size_t smem = (size_t)(2 * H + T) * sizeof(float);
+  if (smem > 48 * 1024) {
+    set_error("attention_pool: 2*H + T = %d floats exceed the 48 KB static budget", 2 * H + T);
+    return B200RNN_ERR_UNSUPPORTED;
+  }
+  attention_pool_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream_)>>>(seq, s_t, s_b, h_n, n_states, B, T, H, w_a,
+                                                                             b_a, ctx);
+  B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return B200RNN_OK;
+}
+
+B200RNN_API int b200rnn_mlp_dropout(const float* x, int B, int n, const float* W, const float* bias, float* out,
+                                    int training, float p, const uint64_t* rng_hdr, uint32_t stream_id,
+                                    void* stream_) {
+  if (!x || !W || !bias || !out || B < 0 || n < 1 || (training && p > 0.f && !rng_hdr)) {
+    set_error("mlp_dropout: bad argument");
+    return B200RNN_ERR_INVALID;
+  }
+  if (B == 0) return B200RNN_OK;
+  if ((size_t)n * sizeof(float) > 48 * 1024) {
+    set_error("mlp_dropout: width %d too large", n);
+    return B200RNN_ERR_UNSUPPORTED;
+  }
+  mlp_dropout_kernel<<<B, 256, (size_t)n * sizeof(float), static_cast<cudaStream_t>(stream_)>>>(
+      x, n, W, bias, out, training, p, rng_hdr, stream_id);
+  B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return B200RNN_OK;
+}
+
+B200RNN_API int b200rnn_fuse_loss_grad(const float* text_feature, int Ht, const float* audio_feature, int Ha,
+                                       const int64_t* labels, int B, const float* W, float* dW, int accumulate,
+                                       float* loss, float* probs, void* stream_) {
+  if (!text_feature || !audio_feature || !labels || !W || !dW || !loss || B < 1 || Ht < 1 || Ha < 1) {
+    set_error("fuse_loss_grad: bad argument");
+    return B200RNN_ERR_INVALID;
+  }
+  const int F = Ht + Ha;
+  const size_t smem = ((size_t)(LOSS_THREADS / 32) * 2 * F + LOSS_THREADS / 32) * sizeof(float);
+  if (F > LOSS_MAXF || smem > 96 * 1024) {
+    set_error("fuse_loss_grad: feature width %d too large", F);
+    return B200RNN_ERR_UNSUPPORTED;
+  }
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(fuse_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  fuse_loss_grad_kernel<<<1, LOSS_THREADS, smem, static_cast<cudaStream_t>(stream_)>>>(
+      text_feature, Ht, audio_feature, Ha, reinterpret_cast<const long long*>(labels), B, W, dW, accumulate, loss, probs);
+  B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return B200RNN_OK;
+}
+
+B200RNN_API int b200rnn_rng_next(uint64_t* hdr, uint64_t* rng_state, uint64_t consume, void* stream_) {
+  if (!hdr || !rng_state) {
+    set_error("rng_next: null pointer");
+    return B200RNN_ERR_INVALID;
+  }
+  return launch_rng_setup(hdr, 0, 0, rng_state, consume, static_cast<cudaStream_t>(stream_));
+}
+
+B200RNN_API int b200rnn_adam(float* p, const float* g, float* m, float* v, float* step, size_t n, float lr, float beta1,
+                             float beta2, float eps, void* stream_) {
+  if (!p || !g || !m || !v || !step) {
+    set_error("adam: null pointer");
+    return B200RNN_ERR_INVALID;
+  }
+  if (n == 0) return B200RNN_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, step, n, lr, beta1, beta2, eps);
+  B200_CUDA_CHECK(cudaGetLastError());
+  adam_step_kernel<<<1, 32, 0, st>>>(step);
+  B200_CUDA_CHECK(cudaGetLastError());
+  count_launch(2);
+  return B200RNN_OK;
+}
+
+}  // extern "C"

@@ -164,6 +164,32 @@ B200RNN_API int b200rnn_gemm_f32(int M, int N, int K, const float* A, int64_t ld
                      void* scratch, size_t scratch_bytes, void* stream);
 
 /*
+ * Model-shell kernels of the fuse step. Each replaces a chain of tiny framework
+ * launches on either side of the encoders; all stream-ordered, caller-owned fp32 buffers.
+ *
+ *  b200rnn_attention_pool : attention_net_with_w (text_bilstm_whole.py:74-99, fuse_net_whole.py:310-334)
+ *       seq [T,B,2H] at t*s_t + b*s_b + c, h_n [n_states,B,H], w_a [H,H], b_a [H]  ->  ctx [B,H]
+ *  b200rnn_mlp_dropout    : Dropout -> Linear(n,n) -> ReLU -> Dropout (fc_out / fc_audio, fuse_net_whole.py:270-275, 288-293)
+ *       dropout masks: Philox streams stream_id and stream_id+1 keyed by rng_hdr = {seed, offset}
+ *  b200rnn_rng_next       : rng_hdr <- *rng_state ; rng_state.offset += consume   (device side, graph replayable)
+ *  b200rnn_fuse_loss_grad : probs = Softmax(cat(tf,af) W^T); loss = CE(tf W[:, :Ht]^T, y) + CE(af W[:, Ht:]^T, y);
+ *       dW (+)= d loss / dW   for W = fc_final.0.weight [2, Ht+Ha]  (fuse_net_whole.py:368-395, 445-454)
+ *  b200rnn_adam           : one torch.optim.Adam step (no weight decay, no amsgrad) over n contiguous parameters;
+ *       m, v, step (a device float counting completed steps) are the optimiser state  (fuse_net_whole.py:416, 456)
+ */
+B200RNN_API int b200rnn_attention_pool(const float* seq, int64_t s_t, int64_t s_b, const float* h_n, int n_states,
+                                       int B, int T, int H, const float* w_a, const float* b_a, float* ctx,
+                                       void* stream);
+B200RNN_API int b200rnn_mlp_dropout(const float* x, int B, int n, const float* W, const float* bias, float* out,
+                                    int training, float p, const uint64_t* rng_hdr, uint32_t stream_id, void* stream);
+B200RNN_API int b200rnn_rng_next(uint64_t* rng_hdr, uint64_t* rng_state, uint64_t consume, void* stream);
+B200RNN_API int b200rnn_fuse_loss_grad(const float* text_feature, int Ht, const float* audio_feature, int Ha,
+                                       const int64_t* labels, int B, const float* W, float* dW, int accumulate,
+                                       float* loss, float* probs, void* stream);
+B200RNN_API int b200rnn_adam(float* p, const float* g, float* m, float* v, float* step, size_t n, float lr,
+                             float beta1, float beta2, float eps, void* stream);
+
+/*
  * Optional device-side timing of the library's own launches (CUDA event pairs on the launching stream),
  * used by bench.py for the roofline figure. kind: 0 = forward recurrence, 1 = backward recurrence,
  * 2 = GEMM, 3 = other. Do not enable while capturing a CUDA graph.

@@ -1,0 +1,153 @@
+"""GPU parity of the fused model-shell kernels against the PyTorch expressions they
+replace (which tests/test_gpu_models.py in turn pins to the reference's goldens)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _fuse_model(train=False):
+    import b200rnn
+
+    torch.manual_seed(0)
+    m = b200rnn.fusion_net(1024, 128, 2, 0.3, 2, 256, 256).to(DEV)
+    for p in m.parameters():
+        p.requires_grad = False
+    m.fc_final[0].weight.requires_grad = True
+    m.train(train)
+    return m
+
+
+def test_attention_pool_kernel_matches_torch():
+    import b200rnn
+    from b200rnn import fused_head
+
+    torch.manual_seed(1)
+    layer = torch.nn.Sequential(torch.nn.Linear(128, 128), torch.nn.ReLU(inplace=True)).to(DEV)
+    seq = torch.randn(30, 17, 256, device=DEV)          # [T,B,2H] time-major
+    h_n = torch.randn(4, 17, 128, device=DEV)
+    got = fused_head.attention_pool(seq, h_n, layer)
+    with torch.no_grad():
+        ref = b200rnn.attention_pool(layer, seq.permute(1, 0, 2), h_n.permute(1, 0, 2))
+    assert (got - ref).abs().max().item() < 1e-5   # values O(1), softmax over N(0,1)*sqrt(H) scores
+
+
+def test_mlp_dropout_kernel_eval_and_train():
+    from b200rnn import fused_head, _lib
+
+    torch.manual_seed(2)
+    lin = torch.nn.Linear(256, 256).to(DEV)
+    x = torch.randn(64, 256, device=DEV)
+    got = fused_head.mlp_dropout(x, lin, 0.3, False, None, 0)
+    with torch.no_grad():
+        ref = torch.relu(lin(x))
+    assert (got - ref).abs().max().item() < 1e-5
+    hdr = torch.tensor([1234, 0], dtype=torch.int64, device=DEV)
+    a = fused_head.mlp_dropout(x, lin, 0.3, True, hdr, 0)
+    b = fused_head.mlp_dropout(x, lin, 0.3, True, hdr, 0)
+    assert torch.equal(a, b), "same {seed, offset} and stream => same masks"
+    hdr2 = torch.tensor([1234, 999], dtype=torch.int64, device=DEV)
+    c = fused_head.mlp_dropout(x, lin, 0.3, True, hdr2, 0)
+    assert not torch.equal(a, c)
+    # output dropout: zeros where ReLU was positive occur at rate ~p
+    base = fused_head.mlp_dropout(x, lin, 0.0, True, hdr, 0)
+    pos = base > 0
+    with torch.no_grad():
+        x1 = torch.ones(4096, 256, device=DEV)
+        lin1 = torch.nn.Linear(256, 256).to(DEV)
+        lin1.weight.fill_(1.0 / 256)
+        lin1.bias.fill_(1.0)
+    d = fused_head.mlp_dropout(x1, lin1, 0.3, True, hdr, 0)
+    drop_rate = (d == 0).float().mean().item()
+    assert 0.28 < drop_rate < 0.32, drop_rate
+    kept = d[d != 0]
+    # kept outputs are (bias + mean of kept&scaled inputs) / (1-p): mean ~ (1 + 1) / 0.7
+    assert abs(kept.mean().item() - 2.0 / 0.7) < 0.02
+    assert pos.any()
+
+
+def test_fuse_loss_grad_and_adam_match_torch():
+    import b200rnn
+    from b200rnn import _lib
+
+    lib = _lib.load()
+    torch.manual_seed(3)
+    B, Ht, Ha = 128, 128, 256
+    tf = torch.randn(B, Ht, device=DEV)
+    af = torch.randn(B, Ha, device=DEV)
+    y = torch.randint(0, 2, (B,), device=DEV)
+    W = (torch.randn(2, Ht + Ha, device=DEV) * 0.05).requires_grad_(True)
+    Wk = W.detach().clone()
+
+    class _M:  # what MyLoss reads
+        fc_final = [type("L", (), {"weight": W})()]
+
+    opt = torch.optim.Adam([W], lr=8e-6)
+    grad = torch.zeros(2 * (Ht + Ha), device=DEV)
+    m = torch.zeros_like(grad)
+    v = torch.zeros_like(grad)
+    step = torch.zeros((), device=DEV)
+    loss_k = torch.zeros((), device=DEV)
+    probs = torch.empty(B, 2, device=DEV)
+    stream = torch.cuda.current_stream().cuda_stream
+    for it in range(4):
+        opt.zero_grad()
+        loss = b200rnn.MyLoss(Ht)(tf, af, y, _M)
+        loss.backward()
+        ref_probs = torch.softmax(torch.cat((tf, af), 1) @ W.detach().t(), dim=1)
+        _lib.check(lib.b200rnn_fuse_loss_grad(tf.data_ptr(), Ht, af.data_ptr(), Ha, y.data_ptr(), B, Wk.data_ptr(),
+                                              grad.data_ptr(), 0, loss_k.data_ptr(), probs.data_ptr(), stream), "loss")
+        assert abs(loss_k.item() - loss.item()) < 2e-6
+        assert (grad.view(2, -1) - W.grad).abs().max().item() < 1e-6 * max(1.0, W.grad.abs().max().item())
+        assert (probs - ref_probs).abs().max().item() < 1e-6
+        opt.step()
+        _lib.check(lib.b200rnn_adam(Wk.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), step.data_ptr(),
+                                    Wk.numel(), 8e-6, 0.9, 0.999, 1e-8, stream), "adam")
+        assert (Wk - W.detach()).abs().max().item() < 1e-7
+    assert step.item() == 4.0
+
+
+def test_fused_fuse_step_equals_generic_path_in_eval():
+    """Dropout off (eval): the fused step must reproduce the generic PyTorch-shell step (which the golden tests pin to
+    the reference): features, probabilities, loss and the updated fc_final weight."""
+    import b200rnn
+
+    m1 = _fuse_model(train=False)
+    m2 = _fuse_model(train=False)
+    m2.load_state_dict(m1.state_dict())
+    torch.manual_seed(5)
+    audio = torch.randn(16, 20, 256, device=DEV)
+    text = torch.randn(16, 6, 1024, device=DEV)
+    y = torch.randint(0, 2, (16,), device=DEV)
+    batch = b200rnn.FuseBatch(audio, text)
+    # generic
+    opt = torch.optim.Adam([m1.fc_final[0].weight], lr=1e-3)
+    tf, af = m1.pretrained_feature(batch)
+    out = m1(torch.cat((tf, af), 1))
+    loss = b200rnn.MyLoss(128)(tf, af, y, m1)
+    loss.backward()
+    opt.step()
+    # fused
+    step = b200rnn.FusedFuseStep(m2, lr=1e-3)
+    tf2, af2 = step.features(batch)
+    probs, loss2 = step(batch, y)
+    torch.cuda.synchronize()
+    assert (tf2 - tf).abs().max().item() < 1e-5 and (af2 - af).abs().max().item() < 1e-4
+    assert (probs - out.detach()).abs().max().item() < 1e-5
+    assert abs(loss2.item() - loss.item()) < 1e-5
+    assert (m2.fc_final[0].weight - m1.fc_final[0].weight).abs().max().item() < 1e-6
+
+
+def test_fused_fuse_step_train_mode_runs_and_varies():
+    import b200rnn
+
+    m = _fuse_model(train=True)
+    step = b200rnn.FusedFuseStep(m)
+    batch = b200rnn.FuseBatch(torch.randn(8, 12, 256, device=DEV), torch.randn(8, 5, 1024, device=DEV))
+    y = torch.randint(0, 2, (8,), device=DEV)
+    _, l1 = step(batch, y)
+    a = l1.item()
+    _, l2 = step(batch, y)
+    assert a != l2.item(), "train-mode dropout must change the features between steps"
+    assert torch.isfinite(m.fc_final[0].weight).all()

@@ -94,29 +94,48 @@ __global__ void attention_pool_kernel(const float* __restrict__ seq, long long s
   }
 }
 
-// ---- out = D2(ReLU(W D1(x) + bias)), one CTA per row ------------------------------------------------------
-__global__ void mlp_dropout_kernel(const float* __restrict__ x, int n, const float* __restrict__ W,
-                                   const float* __restrict__ bias, float* __restrict__ out, int training, float p,
-                                   const uint64_t* __restrict__ hdr, uint32_t stream_id) {
-  extern __shared__ float xs[];  // [n]
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+// ---- out = D2(ReLU(W D1(x) + bias)); a CTA owns MLP_RB batch rows so every weight row is read once per CTA -------
+constexpr int MLP_RB = 8;
+__global__ void __launch_bounds__(256)
+    mlp_dropout_kernel(const float* __restrict__ x, int B, int n, const float* __restrict__ W,
+                       const float* __restrict__ bias, float* __restrict__ out, int training, float p,
+                       const uint64_t* __restrict__ hdr, uint32_t stream_id) {
+  extern __shared__ float xs[];  // [MLP_RB][n]
+  const int b0 = blockIdx.x * MLP_RB, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const bool drop = training && p > 0.f;
   const uint32_t thr = (uint32_t)fminf(p * 4294967296.0f, 4294967295.0f);
   const float scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
-  for (int j = tid; j < n; j += blockDim.x) {
-    float v = x[(size_t)b * n + j];
-    if (drop) v *= keep_scale(hdr, stream_id, (size_t)b * n + j, thr, scale);
-    xs[j] = v;
+  for (int idx = tid; idx < MLP_RB * n; idx += blockDim.x) {
+    const int r = idx / n, j = idx - r * n, b = b0 + r;
+    float v = 0.f;
+    if (b < B) {
+      v = x[(size_t)b * n + j];
+      if (drop) v *= keep_scale(hdr, stream_id, (size_t)b * n + j, thr, scale);
+    }
+    xs[idx] = v;
   }
   __syncthreads();
   for (int i = warp; i < n; i += nw) {
-    float s = 0.f;
-    for (int j = lane; j < n; j += 32) s += W[(size_t)i * n + j] * xs[j];
-    s = warp_sum(s);
-    if (lane == 0) {
-      float v = fmaxf(s + bias[i], 0.f);
-      if (drop) v *= keep_scale(hdr, stream_id + 1, (size_t)b * n + i, thr, scale);
-      out[(size_t)b * n + i] = v;
+    float s[MLP_RB];
+#pragma unroll
+    for (int r = 0; r < MLP_RB; ++r) s[r] = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      const float w = __ldg(W + (size_t)i * n + j);
+#pragma unroll
+      for (int r = 0; r < MLP_RB; ++r) s[r] = fmaf(w, xs[r * n + j], s[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < MLP_RB; ++r) s[r] = warp_sum(s[r]);
+    if (lane < MLP_RB) {
+      const int b = b0 + lane;
+      if (b < B) {
+        float sv = s[0];
+#pragma unroll
+        for (int r = 1; r < MLP_RB; ++r) sv = (lane == r) ? s[r] : sv;
+        float v = fmaxf(sv + bias[i], 0.f);
+        if (drop) v *= keep_scale(hdr, stream_id + 1, (size_t)b * n + i, thr, scale);
+        out[(size_t)b * n + i] = v;
+      }
     }
   }
 }
@@ -124,8 +143,9 @@ __global__ void mlp_dropout_kernel(const float* __restrict__ x, int n, const flo
 // ---- two-head cross entropy on the halves of fc_final.0.weight, its gradient, and the fused softmax output ------
 //   W [2, Ht+Ha];  loss = CE(tf W[:, :Ht]^T, y) + CE(af W[:, Ht:]^T, y)  (mean over B)
 //   dW (+)= d loss / dW ;  probs = softmax(cat(tf,af) W^T)
-constexpr int LOSS_THREADS = 256;
-constexpr int LOSS_MAXF = 1024;  // Ht + Ha
+constexpr int LOSS_THREADS = 512;
+constexpr int LOSS_MAXF = 512;   // Ht + Ha
+constexpr int LOSS_CPL = LOSS_MAXF / 32;  // feature columns per lane
 __global__ void __launch_bounds__(LOSS_THREADS)
     fuse_loss_grad_kernel(const float* __restrict__ tf, int Ht, const float* __restrict__ af, int Ha,
                           const long long* __restrict__ labels, int B, const float* __restrict__ W,
@@ -134,53 +154,62 @@ __global__ void __launch_bounds__(LOSS_THREADS)
   extern __shared__ float dyn[];  // [nw][2][F] per-warp gradient partials, then [nw] loss partials
   const int F = Ht + Ha;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = LOSS_THREADS / 32;
-  float* gpart = dyn + (size_t)warp * 2 * F;
   float* lpart = dyn + (size_t)nw * 2 * F;
-  for (int i = lane; i < 2 * F; i += 32) gpart[i] = 0.f;
-  __syncwarp();
+  // lane owns feature columns lane, lane+32, ... of the concatenated [text | audio] vector
+  float g0[LOSS_CPL], g1[LOSS_CPL];
+#pragma unroll
+  for (int c = 0; c < LOSS_CPL; ++c) g0[c] = g1[c] = 0.f;
   float lsum = 0.f;
   const float invB = 1.f / (float)B;
   for (int b = warp; b < B; b += nw) {
-    const float* t = tf + (size_t)b * Ht;
-    const float* a = af + (size_t)b * Ha;
     float pt0 = 0.f, pt1 = 0.f, pa0 = 0.f, pa1 = 0.f;
-    for (int j = lane; j < Ht; j += 32) {
-      const float v = t[j];
-      pt0 += v * W[j];
-      pt1 += v * W[F + j];
-    }
-    for (int j = lane; j < Ha; j += 32) {
-      const float v = a[j];
-      pa0 += v * W[Ht + j];
-      pa1 += v * W[F + Ht + j];
+    float f[LOSS_CPL];
+#pragma unroll
+    for (int c = 0; c < LOSS_CPL; ++c) {
+      const int j = c * 32 + lane;
+      float v = 0.f;
+      if (j < Ht) {
+        v = tf[(size_t)b * Ht + j];
+        pt0 = fmaf(v, W[j], pt0);
+        pt1 = fmaf(v, W[F + j], pt1);
+      } else if (j < F) {
+        v = af[(size_t)b * Ha + (j - Ht)];
+        pa0 = fmaf(v, W[j], pa0);
+        pa1 = fmaf(v, W[F + j], pa1);
+      }
+      f[c] = v;
     }
     pt0 = warp_sum(pt0); pt1 = warp_sum(pt1); pa0 = warp_sum(pa0); pa1 = warp_sum(pa1);
     const int y = (int)labels[b];
-    // head: text
     float m = fmaxf(pt0, pt1), e0 = expf(pt0 - m), e1 = expf(pt1 - m), z = e0 + e1;
     const float st0 = e0 / z, st1 = e1 / z;
     lsum += (m + logf(z)) - (y == 0 ? pt0 : pt1);
-    // head: audio
     m = fmaxf(pa0, pa1); e0 = expf(pa0 - m); e1 = expf(pa1 - m); z = e0 + e1;
     const float sa0 = e0 / z, sa1 = e1 / z;
     lsum += (m + logf(z)) - (y == 0 ? pa0 : pa1);
     const float dt0 = (st0 - (y == 0 ? 1.f : 0.f)) * invB, dt1 = (st1 - (y == 1 ? 1.f : 0.f)) * invB;
     const float da0 = (sa0 - (y == 0 ? 1.f : 0.f)) * invB, da1 = (sa1 - (y == 1 ? 1.f : 0.f)) * invB;
-    for (int j = lane; j < Ht; j += 32) {
-      const float v = t[j];
-      gpart[j] += dt0 * v;
-      gpart[F + j] += dt1 * v;
-    }
-    for (int j = lane; j < Ha; j += 32) {
-      const float v = a[j];
-      gpart[Ht + j] += da0 * v;
-      gpart[F + Ht + j] += da1 * v;
+#pragma unroll
+    for (int c = 0; c < LOSS_CPL; ++c) {
+      const int j = c * 32 + lane;
+      const bool is_t = j < Ht;
+      g0[c] = fmaf(is_t ? dt0 : da0, f[c], g0[c]);
+      g1[c] = fmaf(is_t ? dt1 : da1, f[c], g1[c]);
     }
     if (probs && lane == 0) {  // Softmax(fc_final(concat)) — used by the reference for accuracy only
       const float l0 = pt0 + pa0, l1 = pt1 + pa1, mm = fmaxf(l0, l1);
       const float x0 = expf(l0 - mm), x1 = expf(l1 - mm);
       probs[(size_t)b * 2 + 0] = x0 / (x0 + x1);
       probs[(size_t)b * 2 + 1] = x1 / (x0 + x1);
+    }
+  }
+  float* gpart = dyn + (size_t)warp * 2 * F;
+#pragma unroll
+  for (int c = 0; c < LOSS_CPL; ++c) {
+    const int j = c * 32 + lane;
+    if (j < F) {
+      gpart[j] = g0[c];
+      gpart[F + j] = g1[c];
     }
   }
   if (lane == 0) lpart[warp] = lsum;
@@ -252,12 +281,12 @@ B200RNN_API int b200rnn_mlp_dropout(const float* x, int B, int n, const float* W
     return B200RNN_ERR_INVALID;
   }
   if (B == 0) return B200RNN_OK;
-  if ((size_t)n * sizeof(float) > 48 * 1024) {
+  if ((size_t)MLP_RB * n * sizeof(float) > 48 * 1024) {
     set_error("mlp_dropout: width %d too large", n);
     return B200RNN_ERR_UNSUPPORTED;
   }
-  mlp_dropout_kernel<<<B, 256, (size_t)n * sizeof(float), static_cast<cudaStream_t>(stream_)>>>(
-      x, n, W, bias, out, training, p, rng_hdr, stream_id);
+  mlp_dropout_kernel<<<(B + MLP_RB - 1) / MLP_RB, 256, (size_t)MLP_RB * n * sizeof(float),
+                       static_cast<cudaStream_t>(stream_)>>>(x, B, n, W, bias, out, training, p, rng_hdr, stream_id);
   B200_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return B200RNN_OK;
@@ -272,13 +301,13 @@ B200RNN_API int b200rnn_fuse_loss_grad(const float* text_feature, int Ht, const 
   }
   const int F = Ht + Ha;
   const size_t smem = ((size_t)(LOSS_THREADS / 32) * 2 * F + LOSS_THREADS / 32) * sizeof(float);
-  if (F > LOSS_MAXF || smem > 96 * 1024) {
+  if (F > LOSS_MAXF || smem > 200 * 1024) {
     set_error("fuse_loss_grad: feature width %d too large", F);
     return B200RNN_ERR_UNSUPPORTED;
   }
   static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
-    B200_CUDA_CHECK(cudaFuncSetAttribute(fuse_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  if (!attr) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(fuse_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   fuse_loss_grad_kernel<<<1, LOSS_THREADS, smem, static_cast<cudaStream_t>(stream_)>>>(

@@ -94,45 +94,52 @@ __global__ void attention_pool_kernel(const float* __restrict__ seq, long long s
   }
 }
 
-// ---- out = D2(ReLU(W D1(x) + bias)); a CTA owns MLP_RB batch rows so every weight row is read once per CTA -------
-constexpr int MLP_RB = 8;
+// ---- out = D2(ReLU(W D1(x) + bias)) as a small tiled GEMM: CTA tile = 32 outputs x 32 batch rows ---------------
+// Both operand tiles are staged in shared memory with bulk coalesced loads (no dependent global-load chains; the
+// first version, one warp-dot per output, spent its time waiting on one L2 round trip per 32 columns).
+constexpr int MLP_TI = 32, MLP_TB = 32;
 __global__ void __launch_bounds__(256)
     mlp_dropout_kernel(const float* __restrict__ x, int B, int n, const float* __restrict__ W,
                        const float* __restrict__ bias, float* __restrict__ out, int training, float p,
                        const uint64_t* __restrict__ hdr, uint32_t stream_id) {
-  extern __shared__ float xs[];  // [MLP_RB][n]
-  const int b0 = blockIdx.x * MLP_RB, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  extern __shared__ float sm[];
+  const int ld = n + 1;                // +1: conflict-free column walks
+  float* Ws = sm;                      // [MLP_TI][ld]
+  float* xs = sm + MLP_TI * ld;        // [MLP_TB][ld]
+  const int i0 = blockIdx.x * MLP_TI, b0 = blockIdx.y * MLP_TB, tid = threadIdx.x;
   const bool drop = training && p > 0.f;
   const uint32_t thr = (uint32_t)fminf(p * 4294967296.0f, 4294967295.0f);
   const float scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
-  for (int idx = tid; idx < MLP_RB * n; idx += blockDim.x) {
+  for (int idx = tid; idx < MLP_TI * n; idx += blockDim.x) {
+    const int r = idx / n, j = idx - r * n;
+    Ws[r * ld + j] = (i0 + r < n) ? __ldg(W + (size_t)(i0 + r) * n + j) : 0.f;
+  }
+  for (int idx = tid; idx < MLP_TB * n; idx += blockDim.x) {
     const int r = idx / n, j = idx - r * n, b = b0 + r;
     float v = 0.f;
     if (b < B) {
       v = x[(size_t)b * n + j];
       if (drop) v *= keep_scale(hdr, stream_id, (size_t)b * n + j, thr, scale);
     }
-    xs[idx] = v;
+    xs[r * ld + j] = v;
   }
   __syncthreads();
-  for (int i = warp; i < n; i += nw) {
-    float s[MLP_RB];
+  const int ti = tid & 31, tb = tid >> 5;  // output column ti, batch rows tb, tb+8, tb+16, tb+24
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* wrow = Ws + ti * ld;
+  for (int j = 0; j < n; ++j) {
+    const float w = wrow[j];
 #pragma unroll
-    for (int r = 0; r < MLP_RB; ++r) s[r] = 0.f;
-    for (int j = lane; j < n; j += 32) {
-      const float w = __ldg(W + (size_t)i * n + j);
+    for (int r = 0; r < 4; ++r) acc[r] = fmaf(w, xs[(tb + 8 * r) * ld + j], acc[r]);
+  }
+  const int i = i0 + ti;
+  if (i < n) {
+    const float bi = bias[i];
 #pragma unroll
-      for (int r = 0; r < MLP_RB; ++r) s[r] = fmaf(w, xs[r * n + j], s[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < MLP_RB; ++r) s[r] = warp_sum(s[r]);
-    if (lane < MLP_RB) {
-      const int b = b0 + lane;
+    for (int r = 0; r < 4; ++r) {
+      const int b = b0 + tb + 8 * r;
       if (b < B) {
-        float sv = s[0];
-#pragma unroll
-        for (int r = 1; r < MLP_RB; ++r) sv = (lane == r) ? s[r] : sv;
-        float v = fmaxf(sv + bias[i], 0.f);
+        float v = fmaxf(acc[r] + bi, 0.f);
         if (drop) v *= keep_scale(hdr, stream_id + 1, (size_t)b * n + i, thr, scale);
         out[(size_t)b * n + i] = v;
       }
@@ -281,12 +288,19 @@ B200RNN_API int b200rnn_mlp_dropout(const float* x, int B, int n, const float* W
     return B200RNN_ERR_INVALID;
   }
   if (B == 0) return B200RNN_OK;
-  if ((size_t)MLP_RB * n * sizeof(float) > 48 * 1024) {
+  const size_t smem = (size_t)(MLP_TI + MLP_TB) * (n + 1) * sizeof(float);
+  if (smem > 200 * 1024) {
     set_error("mlp_dropout: width %d too large", n);
     return B200RNN_ERR_UNSUPPORTED;
   }
-  mlp_dropout_kernel<<<(B + MLP_RB - 1) / MLP_RB, 256, (size_t)MLP_RB * n * sizeof(float),
-                       static_cast<cudaStream_t>(stream_)>>>(x, B, n, W, bias, out, training, p, rng_hdr, stream_id);
+  static bool attr = false;
+  if (!attr) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(mlp_dropout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  dim3 grid((n + MLP_TI - 1) / MLP_TI, (B + MLP_TB - 1) / MLP_TB);
+  mlp_dropout_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream_)>>>(x, B, n, W, bias, out, training, p, rng_hdr,
+                                                                          stream_id);
   B200_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return B200RNN_OK;

@@ -47,6 +47,25 @@ LR = 8e-6                                                               # fuse_n
 N_ROTATE = 4  # distinct resident input batches; 4 x 31.5 MB of inputs + per-step intermediates > 126 MB L2
 
 
+_REAL_STDOUT_FD = None
+
+
+def _protect_stdout() -> None:
+    """The contract is ONE JSON line on stdout; libraries (NCCL prints its version banner there) must not add to it.
+    fd 1 is pointed at stderr for the life of the process; the JSON goes to the saved descriptor."""
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT_FD if _REAL_STDOUT_FD is not None else 1
+    os.write(fd, data)
+
+
 def _log(msg: str) -> None:
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
@@ -162,7 +181,7 @@ def run_reference(args) -> None:
                                    "torch tensors; rank 0 only)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -523,9 +542,17 @@ def run_ours(args) -> None:
         alg_flops = 2 * B * T * 3 * H * H                       # recurrent contraction of this launch
         t_launch = rec_ms / max(rec_n, 1) * 1e-3
         achieved = alg_bytes / t_launch / 1e9
+        traffic = None   # dram bytes per launch from the committed ncu --set full capture of this kernel
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
+                traffic = json.load(fh)["r01_ncu_rec_fwd.csv"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line["roofline"] = {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": traffic, "traffic_source": "profiles/r01_ncu_rec_fwd.csv (ncu --set full, cold L2: includes the "
+                                                  "x-projection read that is an L2 hit in the real step)",
+            "peak_source": peak_src,
             "kernel": "rec_fwd_kernel<GRU,H=256> (persistent cluster recurrence, one launch per layer)",
             "launch_ms": t_launch * 1e3, "launches_timed": rec_n,
             "algorithmic_bytes_per_launch": alg_bytes,
@@ -554,7 +581,7 @@ def run_ours(args) -> None:
                 "sample": f"{nst} train steps of B={B_PER_GPU} after 1 warm-up ({ms:.0f} ms/step) with the oracle port "
                           f"(oracle/ref_models.py on stock torch.nn CPU kernels, {cores} threads); with the reference's "
                           f"list->tensor conversion (fuse_net_whole.py:343) it is {v2:.1f} seq/s ({ms2:.0f} ms/step)"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     # Teardown: tearing an NCCL communicator down while captured graphs still hold its kernels can dead-lock
     # (observed: 2-rank run hung in destroy_process_group after printing). Drop the graphs, sync, leave hard.
     graphs.clear()
@@ -616,6 +643,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the secondary module timings")
     args = ap.parse_args()
+    _protect_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args)

@@ -12,9 +12,10 @@ from .staging import FuseBatch, PinnedStager, stage_fuse_batch
 from .dp import GradBucket, broadcast_parameters, shard_batch
 from .models import AudioBiLSTM, MyLoss, TextBiLSTM, attention_pool, fusion_net
 from .fused_head import FusedFuseStep
+from .optim import FlatAdamW
 
 __all__ = [
     "GRU", "LSTM", "install", "uninstall", "from_torch", "rnn_forward", "gemm", "RNNConfig", "B200RNNError",
     "AudioBiLSTM", "TextBiLSTM", "fusion_net", "MyLoss", "attention_pool", "FuseBatch", "PinnedStager",
-    "stage_fuse_batch", "GradBucket", "broadcast_parameters", "shard_batch", "FusedFuseStep",
+    "stage_fuse_batch", "GradBucket", "broadcast_parameters", "shard_batch", "FusedFuseStep", "FlatAdamW",
 ]

@@ -33,6 +33,7 @@ SYMBOLS = (
     "b200rnn_rng_next",
     "b200rnn_fuse_loss_grad",
     "b200rnn_adam",
+    "b200rnn_adamw",
     "b200rnn_profile",
     "b200rnn_profile_read",
 )
@@ -130,6 +131,9 @@ def load() -> ctypes.CDLL:
     lib.b200rnn_adam.restype = c_int
     lib.b200rnn_adam.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
                                  c_float, c_void_p]
+    lib.b200rnn_adamw.restype = c_int
+    lib.b200rnn_adamw.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
+                                  c_float, c_float, c_float, c_int, c_void_p]
     lib.b200rnn_profile.restype = c_int
     lib.b200rnn_profile.argtypes = [c_int]
     lib.b200rnn_profile_read.restype = c_int

@@ -1,0 +1,92 @@
+"""Flat, fused AdamW for the training loops of the reference.
+
+``audio_gru_whole.py:247-255, 307`` / ``text_bilstm_whole.py:237-245, 303`` build ``optim.AdamW`` with two parameter
+groups (weight decay 1e-5, and 0 for names containing ``ln``). ``FlatAdamW`` re-homes every parameter of a group as a
+view of ONE contiguous buffer, keeps ``.grad``, ``m`` and ``v`` the same way, and updates a whole group with a single
+kernel launch (``b200rnn_adamw``) — the flat gradient buffer is also exactly what the data-parallel step all-reduces
+(one collective per step), and the ``1/world`` averaging is folded into the update.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .modules import _B200RNNBase
+
+
+class _Group:
+    def __init__(self, params: List[torch.nn.Parameter], weight_decay: float):
+        self.params = params
+        self.weight_decay = float(weight_decay)
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                self.flat_p[off:off + k].copy_(p.reshape(-1))
+                p.data = self.flat_p[off:off + k].view_as(p)       # parameter now lives in the flat buffer
+                p.grad = self.flat_g[off:off + k].view_as(p)       # autograd accumulates into the flat gradient
+                off += k
+
+
+class FlatAdamW:
+    """``torch.optim.AdamW`` semantics (decoupled weight decay, no amsgrad) over flat parameter groups.
+
+    ``groups``: sequence of ``{"params": [...], "weight_decay": wd}`` like the reference's ``optimizer_grouped_parameters``.
+    """
+
+    def __init__(self, groups: Sequence[dict], lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+                 model: Optional[torch.nn.Module] = None, process_group=None):
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.groups = [_Group([p for p in g["params"] if p.requires_grad], g.get("weight_decay", 0.0))
+                       for g in groups if any(p.requires_grad for p in g["params"])]
+        dev = self.groups[0].flat_p.device
+        self.step_count = torch.zeros((), dtype=torch.float32, device=dev)
+        self.process_group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        if model is not None:   # RNN wgrad kernels write straight into the flat gradient views
+            views = {p.data_ptr(): p.grad for g in self.groups for p in g.params}
+            for mod in model.modules():
+                if isinstance(mod, _B200RNNBase):
+                    mod._grad_sink = lambda weights, _v=views: [_v.get(w.data_ptr()) for w in weights]
+
+    @classmethod
+    def like_reference(cls, model: torch.nn.Module, lr: float, weight_decay: float = 1e-5, **kw) -> "FlatAdamW":
+        """The grouping of audio_gru_whole.py:247-255: no decay for parameters whose name contains 'ln'."""
+        named = list(model.named_parameters())
+        decay = [p for n, p in named if "ln" not in n]
+        no_decay = [p for n, p in named if "ln" in n]
+        groups = [{"params": decay, "weight_decay": weight_decay}]
+        if no_decay:
+            groups.append({"params": no_decay, "weight_decay": 0.0})
+        return cls(groups, lr, model=model, **kw)
+
+    def zero_grad(self) -> None:
+        for g in self.groups:
+            g.flat_g.zero_()
+
+    def allreduce(self) -> None:
+        """One collective per group (the reference's two groups could be merged; kept separate for clarity)."""
+        if self.world > 1:
+            for g in self.groups:
+                dist.all_reduce(g.flat_g, op=dist.ReduceOp.SUM, group=self.process_group)
+
+    @torch.no_grad()
+    def step(self) -> None:
+        lib = _lib.load()
+        stream = torch.cuda.current_stream().cuda_stream
+        scale = 1.0 / self.world
+        for i, g in enumerate(self.groups):
+            last = i == len(self.groups) - 1
+            _lib.check(lib.b200rnn_adamw(g.flat_p.data_ptr(), g.flat_g.data_ptr(), g.m.data_ptr(), g.v.data_ptr(),
+                                         self.step_count.data_ptr(), g.flat_p.numel(), self.lr, self.betas[0],
+                                         self.betas[1], self.eps, g.weight_decay, scale, int(last), stream),
+                       "b200rnn_adamw")

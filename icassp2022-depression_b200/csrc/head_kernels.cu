@@ -234,19 +234,21 @@ __global__ void __launch_bounds__(LOSS_THREADS)
 }
 
 // ---- Adam (torch.optim.Adam defaults: no weight decay, no amsgrad), step counter on the device ------------------
+// weight_decay is decoupled (torch.optim.AdamW: p *= 1 - lr*wd before the update; 0 gives torch.optim.Adam);
+// grad_scale folds the 1/world averaging of the data-parallel all-reduce into the same pass.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, const float* __restrict__ step, size_t n, float lr, float b1,
-                            float b2, float eps) {
+                            float b2, float eps, float weight_decay, float grad_scale) {
   const float t = *step + 1.f;  // the increment itself is done by adam_step_kernel after this launch
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
-  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * weight_decay;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float gi = g[i];
+    const float gi = g[i] * grad_scale;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+    p[i] = p[i] * decay - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
   }
 }
 __global__ void adam_step_kernel(float* step) {
@@ -339,22 +341,32 @@ B200RNN_API int b200rnn_rng_next(uint64_t* hdr, uint64_t* rng_state, uint64_t co
   return launch_rng_setup(hdr, 0, 0, rng_state, consume, static_cast<cudaStream_t>(stream_));
 }
 
-B200RNN_API int b200rnn_adam(float* p, const float* g, float* m, float* v, float* step, size_t n, float lr, float beta1,
-                             float beta2, float eps, void* stream_) {
+B200RNN_API int b200rnn_adamw(float* p, const float* g, float* m, float* v, float* step, size_t n, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                              int advance_step, void* stream_) {
   if (!p || !g || !m || !v || !step) {
-    set_error("adam: null pointer");
+    set_error("adamw: null pointer");
     return B200RNN_ERR_INVALID;
   }
-  if (n == 0) return B200RNN_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, step, n, lr, beta1, beta2, eps);
-  B200_CUDA_CHECK(cudaGetLastError());
-  adam_step_kernel<<<1, 32, 0, st>>>(step);
-  B200_CUDA_CHECK(cudaGetLastError());
-  count_launch(2);
+  if (n > 0) {
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, step, n, lr, beta1, beta2, eps, weight_decay, grad_scale);
+    B200_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  if (advance_step) {  // several parameter groups share one step counter: advance it after the last group
+    adam_step_kernel<<<1, 32, 0, st>>>(step);
+    B200_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
   return B200RNN_OK;
+}
+
+B200RNN_API int b200rnn_adam(float* p, const float* g, float* m, float* v, float* step, size_t n, float lr, float beta1,
+                             float beta2, float eps, void* stream_) {
+  return b200rnn_adamw(p, g, m, v, step, n, lr, beta1, beta2, eps, 0.f, 1.f, 1, stream_);
 }
 
 }  // extern "C"

@@ -188,6 +188,12 @@ B200RNN_API int b200rnn_fuse_loss_grad(const float* text_feature, int Ht, const 
                                        float* loss, float* probs, void* stream);
 B200RNN_API int b200rnn_adam(float* p, const float* g, float* m, float* v, float* step, size_t n, float lr,
                              float beta1, float beta2, float eps, void* stream);
+/* AdamW over one flat parameter group (audio_gru_whole.py:247-255, 307: optim.AdamW with a decay and a no-decay group):
+ * p = p*(1 - lr*weight_decay) - lr/(1-b1^t) * m / (sqrt(v/(1-b2^t)) + eps), with g scaled by grad_scale (the 1/world of
+ * the data-parallel mean) on the fly. Groups sharing `step` pass advance_step = 1 only for the last group. */
+B200RNN_API int b200rnn_adamw(float* p, const float* g, float* m, float* v, float* step, size_t n, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                              int advance_step, void* stream);
 
 /*
  * Optional device-side timing of the library's own launches (CUDA event pairs on the launching stream),

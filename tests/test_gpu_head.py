@@ -151,3 +151,40 @@ def test_fused_fuse_step_train_mode_runs_and_varies():
     _, l2 = step(batch, y)
     assert a != l2.item(), "train-mode dropout must change the features between steps"
     assert torch.isfinite(m.fc_final[0].weight).all()
+
+
+def test_flat_adamw_matches_torch_adamw_with_reference_grouping():
+    """audio_gru_whole.py:247-255, 307: AdamW(lr 6e-6; wd 1e-5, and 0 for 'ln'); three full training steps."""
+    import copy
+
+    import b200rnn
+
+    torch.manual_seed(11)
+    cfg = dict(num_classes=2, dropout=0.0, rnn_layers=2, embedding_size=256, hidden_dims=256)
+    m1 = b200rnn.AudioBiLSTM(cfg).to(DEV).train()
+    m2 = copy.deepcopy(m1)
+    named = list(m1.named_parameters())
+    groups = [{"params": [p for n, p in named if "ln" not in n], "weight_decay": 1e-2},
+              {"params": [p for n, p in named if "ln" in n], "weight_decay": 0.0}]
+    lr = 1e-3   # large enough that three steps move the weights measurably
+    opt1 = torch.optim.AdamW(groups, lr=lr)
+    opt2 = b200rnn.FlatAdamW.like_reference(m2, lr=lr, weight_decay=1e-2)
+    x = torch.randn(8, 10, 256, device=DEV)
+    y = torch.randint(0, 2, (8,), device=DEV)
+    crit = torch.nn.CrossEntropyLoss()
+    for _ in range(3):
+        opt1.zero_grad()
+        crit(m1(x), y).backward()
+        opt1.step()
+        opt2.zero_grad()
+        crit(m2(x), y).backward()
+        opt2.step()
+    torch.cuda.synchronize()
+    for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        if a.grad is None:
+            continue
+        assert (a - b).abs().max().item() <= 2e-6 + 1e-4 * lr, n   # 3 steps of size <= lr each
+    assert opt2.step_count.item() == 3.0
+    # the parameters really live in the flat buffers now
+    g0 = opt2.groups[0]
+    assert all(p.data_ptr() >= g0.flat_p.data_ptr() for p in g0.params)

@@ -99,7 +99,8 @@ def load() -> ctypes.CDLL:
         c_void_p,                                    # stream
     ]
     lib.b200rnn_forward_fused.restype = c_int
-    lib.b200rnn_forward_fused.argtypes = lib.b200rnn_forward.argtypes[:-1] + [c_void_p, c_void_p, c_float, c_void_p, c_void_p]
+    lib.b200rnn_forward_fused.argtypes = lib.b200rnn_forward.argtypes[:-1] + [c_void_p, c_void_p, c_float, c_void_p,
+                                                                              c_void_p, c_void_p]
     lib.b200rnn_backward.restype = c_int
     lib.b200rnn_backward.argtypes = [
         POINTER(Desc), c_void_p, c_int64, c_int64,   # desc, x, strides
@@ -110,6 +111,7 @@ def load() -> ctypes.CDLL:
         c_void_p, c_void_p,                          # reserve, scratch
         c_void_p, c_int64, c_int64,                  # dx
         POINTER(c_void_p),                           # dparams
+        c_void_p,                                    # lengths
         c_void_p,                                    # stream
     ]
     lib.b200rnn_gemm_f32.restype = c_int

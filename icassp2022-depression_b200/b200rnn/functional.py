@@ -63,7 +63,7 @@ class _RNNFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_tm: torch.Tensor, cfg: RNNConfig, rng_state: Optional[torch.Tensor], grad_sink,
-                *weights: torch.Tensor):
+                lengths: Optional[torch.Tensor], *weights: torch.Tensor):
         lib = _lib.load()
         T, B, _ = x_tm.shape
         H, L, D = cfg.hidden_size, cfg.num_layers, cfg.num_dirs
@@ -83,11 +83,12 @@ class _RNNFunction(torch.autograd.Function):
         c_n = torch.empty(L * D, B, H, dtype=torch.float32, device=dev) if cfg.mode == _lib.LSTM else None
         params = _lib.ptr_array([w.data_ptr() for w in weights])
         if B > 0 and T > 0:
-            rc = lib.b200rnn_forward(
+            rc = lib.b200rnn_forward_fused(
                 ctypes.byref(desc), x_tm.data_ptr(), x_tm.stride(0), x_tm.stride(1), params,
                 y.data_ptr(), ys_t, ys_b, h_n.data_ptr(), c_n.data_ptr() if c_n is not None else None,
                 reserve.data_ptr() if save else None, scratch.data_ptr(),
-                0, 0, rng_state.data_ptr() if rng_state is not None else None, _stream_ptr())
+                0, 0, rng_state.data_ptr() if rng_state is not None else None, None, None, 0.0, None,
+                lengths.data_ptr() if lengths is not None else None, _stream_ptr())
             _lib.check(rc, "b200rnn_forward")
         else:
             h_n.zero_()
@@ -97,6 +98,7 @@ class _RNNFunction(torch.autograd.Function):
             ctx.cfg = cfg
             ctx.grad_sink = grad_sink
             ctx.ys = (ys_t, ys_b)
+            ctx.lengths = lengths
             ctx.save_for_backward(x_tm, y, reserve, *weights)
         if c_n is None:
             return y, h_n
@@ -133,7 +135,7 @@ class _RNNFunction(torch.autograd.Function):
         # weight gradients: either straight into caller-provided views (a flat all-reduce bucket) or into one
         # fresh flat buffer that is returned to autograd as views
         sink = ctx.grad_sink
-        w_needed = [ctx.needs_input_grad[4 + i] for i in range(len(weights))]
+        w_needed = [ctx.needs_input_grad[5 + i] for i in range(len(weights))]
         grads_out: list = [None] * len(weights)
         accumulate = False
         if sink is not None:
@@ -167,17 +169,17 @@ class _RNNFunction(torch.autograd.Function):
                 reserve.data_ptr(), scratch.data_ptr(),
                 dx.data_ptr() if dx is not None else None,
                 dx.stride(0) if dx is not None else 0, dx.stride(1) if dx is not None else 0,
-                dparams, _stream_ptr())
+                dparams, ctx.lengths.data_ptr() if ctx.lengths is not None else None, _stream_ptr())
             _lib.check(rc, "b200rnn_backward")
         else:
             for g in grads_out:
                 if g is not None:
                     g.zero_()
-        return (dx, None, None, None, *grads_out)
+        return (dx, None, None, None, None, *grads_out)
 
 
 def rnn_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNNConfig,
-                rng_state: Optional[torch.Tensor] = None, grad_sink=None):
+                rng_state: Optional[torch.Tensor] = None, grad_sink=None, lengths: Optional[torch.Tensor] = None):
     """Run the multi-layer GRU/LSTM. ``x`` is [T,B,I] (or [B,T,I] if ``cfg.batch_first``), any strides.
 
     Returns ``(y, h_n)`` for GRU and ``(y, h_n, c_n)`` for LSTM, laid out like torch.nn.GRU/LSTM outputs.
@@ -193,7 +195,9 @@ def rnn_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNNConfig
         raise RuntimeError(f"input.size(-1) must be equal to input_size. Expected {cfg.input_size}, got {x.size(2)}")
     x_tm = x.transpose(0, 1) if cfg.batch_first else x
     x_tm = _tm_view(x_tm)
-    return _RNNFunction.apply(x_tm, cfg, rng_state, grad_sink, *weights)
+    if lengths is not None:
+        lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
+    return _RNNFunction.apply(x_tm, cfg, rng_state, grad_sink, lengths, *weights)
 
 
 @torch.no_grad()
@@ -231,7 +235,7 @@ def rnn_forward_fused(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNN
         h_n.data_ptr(), c_n.data_ptr() if c_n is not None else None, None, scratch.data_ptr(), 0, 0,
         rng_state.data_ptr() if rng_state is not None else None,
         ln_weight.data_ptr() if ln_weight is not None else None, ln_bias.data_ptr() if ln_bias is not None else None,
-        float(ln_eps), pool_ptr, _stream_ptr())
+        float(ln_eps), pool_ptr, None, _stream_ptr())
     _lib.check(rc, "b200rnn_forward_fused")
     return (out, h_n) if c_n is None else (out, h_n, c_n)
 

@@ -10,8 +10,8 @@ default init U(-1/sqrt(H), 1/sqrt(H)) (rnn.py:308-311) and the ``forward`` retur
   fuse_net_whole.py:266-268, 281-286) construct them unchanged once :func:`install` has rebound
   ``torch.nn.GRU`` / ``torch.nn.LSTM``.
 
-Unused-by-the-reference features raise ``NotImplementedError``: PackedSequence, proj_size, bias=False,
-non-None initial state, unbatched 2-D input.
+``PackedSequence`` input is supported (per-sequence lengths in the kernels). Unused-by-the-reference features that
+raise ``NotImplementedError``: proj_size, bias=False, non-None initial state, unbatched 2-D input.
 """
 from __future__ import annotations
 
@@ -131,16 +131,33 @@ class _B200RNNBase(nn.Module):
                          num_layers=self.num_layers, num_dirs=2 if self.bidirectional else 1,
                          dropout=self.dropout, training=self.training, batch_first=self.batch_first)
 
+    def _run_packed(self, packed):
+        """PackedSequence path (ragged DAIC-style sequences): pad, run with per-sequence lengths, re-pack exactly like
+        torch (same batch_sizes / sorted_indices; h_n, c_n in the caller's original batch order)."""
+        rnn_utils = nn.utils.rnn
+        padded, lengths = rnn_utils.pad_packed_sequence(packed, batch_first=self.batch_first)
+        out = rnn_forward(padded, self._flat_weights, self._config(), self._rng_state, self._grad_sink, lengths=lengths)
+        y = out[0]
+        bdim = 0 if self.batch_first else 1
+        if packed.sorted_indices is not None:
+            y = y.index_select(bdim, packed.sorted_indices)
+            lens_sorted = lengths.index_select(0, packed.sorted_indices.cpu())
+        else:
+            lens_sorted = lengths
+        repacked = rnn_utils.pack_padded_sequence(y, lens_sorted, batch_first=self.batch_first, enforce_sorted=True)
+        y_packed = rnn_utils.PackedSequence(repacked.data, packed.batch_sizes, packed.sorted_indices,
+                                            packed.unsorted_indices)
+        return (y_packed, *out[1:])
+
     def _run(self, input, hx):
-        if isinstance(input, nn.utils.rnn.PackedSequence):
-            raise NotImplementedError("b200rnn: PackedSequence input is not implemented (unused by the reference)")
         if hx is not None:
             raise NotImplementedError("b200rnn: a non-None initial state is not implemented (the reference "
                                       "always starts from zeros, rnn.py:1432-1440)")
+        if isinstance(input, nn.utils.rnn.PackedSequence):
+            return self._run_packed(input)
         if input.dim() != 3:
             raise NotImplementedError("b200rnn: unbatched 2-D input is not implemented")
         return rnn_forward(input, self._flat_weights, self._config(), self._rng_state, self._grad_sink)
-
 
     def forward_ln_sum(self, input: torch.Tensor, ln: Optional[nn.LayerNorm] = None) -> torch.Tensor:
         """``self(ln(input))[0].sum(dim=time)`` — the audio branch of fuse_net_whole.py:360-362 / fuse_net.py:338-339.

@@ -233,7 +233,7 @@ B200RNN_API int b200rnn_forward_fused(const b200rnn_desc* desc, const float* x, 
                                       const float* const* params, float* y, int64_t ys_t, int64_t ys_b, float* h_n,
                                       float* c_n, void* reserve, void* scratch, uint64_t seed, uint64_t offset,
                                       uint64_t* rng_state, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                                      float* y_pool, void* stream_) {
+                                      float* y_pool, const int32_t* lengths, void* stream_) {
   Dims d;
   int rc = check_desc(desc, &d);
   if (rc) return rc;
@@ -360,6 +360,7 @@ B200RNN_API int b200rnn_forward_fused(const b200rnn_desc* desc, const float* x, 
     rp.h_n = h_n + (size_t)l * d.D * d.B * d.H;
     rp.c_n = c_n ? c_n + (size_t)l * d.D * d.B * d.H : nullptr;
     rp.trace = g_trace;
+    rp.lengths = lengths;
     rc = launch_rec_fwd(rp, st);
     if (rc) return rc;
     if (drop && l + 1 < d.L) {  // K7; keeps the raw output when it is needed by backward, else in place
@@ -382,14 +383,14 @@ B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_
                                 float* c_n, void* reserve, void* scratch, uint64_t seed, uint64_t offset,
                                 uint64_t* rng_state, void* stream_) {
   return b200rnn_forward_fused(desc, x, xs_t, xs_b, params, y, ys_t, ys_b, h_n, c_n, reserve, scratch, seed, offset,
-                               rng_state, nullptr, nullptr, 0.f, nullptr, stream_);
+                               rng_state, nullptr, nullptr, 0.f, nullptr, nullptr, stream_);
 }
 
 B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64_t xs_t, int64_t xs_b,
                                  const float* const* params, const float* y, int64_t ys_t, int64_t ys_b,
                                  const float* dy, int64_t dys_t, int64_t dys_b, const float* dh_n,
                                  const float* dc_n, const void* reserve, void* scratch, float* dx, int64_t dxs_t,
-                                 int64_t dxs_b, float* const* dparams, void* stream_) {
+                                 int64_t dxs_b, float* const* dparams, const int32_t* lengths, void* stream_) {
   Dims d;
   int rc = check_desc(desc, &d);
   if (rc) return rc;
@@ -443,6 +444,7 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
       bp.dghn[k] = S + sl.b_dghn[k];
       bp.dbias_part[k] = S + sl.b_bpart[k];
     }
+    bp.lengths = lengths;
     rc = launch_rec_bwd(bp, st);
     if (rc) return rc;
 

@@ -18,6 +18,7 @@ struct RecFwdParams {
   float* h_n;                // [D,B,H] of this layer
   float* c_n;                // [D,B,H] of this layer (LSTM) or NULL
   long long* trace;          // debug: per-step phase timestamps of CTA 0 / warp 0 (NULL = off), [T][8]
+  const int* lengths;        // optional [B]: valid steps per sequence (PackedSequence semantics); NULL = all T
 };
 
 struct RecBwdParams {
@@ -36,6 +37,7 @@ struct RecBwdParams {
   float* dghn[2];            // out (GRU only): [T,B,H] gradient w.r.t. (W_hn h + b_hn) = dn * r
   float* dbias_part[2];      // out: [nslices][(G+1)*H] per-slice column sums (rows 0..G*H: dGi; GRU tail H: dghn)
   int nslices_out;           // filled by the launcher
+  const int* lengths;        // optional [B], as in the forward
 };
 
 // number of batch slices the launcher will use for this shape (needed to size dbias_part)

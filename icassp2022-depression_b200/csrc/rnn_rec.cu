@@ -93,7 +93,8 @@ __device__ __forceinline__ void allgather_units(float val, float* vec_local, int
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int MODE, int H, int C, int BS, int KL, int UPL, int RG>
+// VL = true: per-sequence lengths (PackedSequence semantics): past its length a sequence keeps its state and emits 0
+template <int MODE, int H, int C, int BS, int KL, int UPL, int RG, bool VL = false>
 __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     rec_fwd_kernel(const RecFwdParams p, const int nslices) {
   using Cfg = RecCfg<MODE, H, C, BS, KL, UPL, RG>;
@@ -146,6 +147,10 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
   const float bhn = (MODE == B200RNN_GRU) ? p.b_hh[dir][2 * H + j] : 0.f;
 
   float h_prev = 0.f, c_prev = 0.f, h_sum = 0.f;
+  int len_b = T;
+  if constexpr (VL) {
+    if (valid) len_b = p.lengths[b];
+  }
   float gi[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) gi[g] = 0.f;
@@ -219,19 +224,32 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
       const float hn = acc[2][0][0] + bhn;
       const float n = tanh_f(gi[2] + r * hn);
       hnew = n + z * (h_prev - n);
+      if constexpr (VL) {
+        if (t >= len_b) hnew = h_prev;
+      }
       s0 = r; s1 = z; s2 = n; sx = hn;
     } else {
       const float ig = sigmoid_f(gi[0] + acc[0][0][0]);
       const float fg = sigmoid_f(gi[1] + acc[1][0][0]);
       const float gg = tanh_f(gi[2] + acc[2][0][0]);
       const float og = sigmoid_f(gi[G - 1] + acc[G - 1][0][0]);
-      const float cnew = fg * c_prev + ig * gg;
+      float cnew = fg * c_prev + ig * gg;
       hnew = og * tanh_f(cnew);
+      if constexpr (VL) {
+        if (t >= len_b) {
+          cnew = c_prev;
+          hnew = h_prev;
+        }
+      }
       c_prev = cnew;
       s0 = ig; s1 = fg; s2 = gg; s3 = og; sx = cnew;
     }
     h_prev = hnew;
-    h_sum += hnew;
+    float yv = hnew;  // what the caller sees at this step
+    if constexpr (VL) {
+      if (t >= len_b) yv = 0.f;
+    }
+    h_sum += yv;
     if (tr) trow[4] = clock64() + (long long)(hnew == 12345.678f);
 
     if (step + 1 < T)
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
 
     // off the critical path: global stores of this step, prefetch of the next step's x-projection
     if (valid) {
-      if (p.y) p.y[(long long)t * p.y_st + (long long)b * p.y_sb + dir * H + j] = hnew;
+      if (p.y) p.y[(long long)t * p.y_st + (long long)b * p.y_sb + dir * H + j] = yv;
       if (p.training) {
         float* gp = gates + ((size_t)t * B + b) * GH + j;
         gp[0] = s0;
@@ -290,7 +308,7 @@ __global__ void whh_prep_kernel(const float* __restrict__ w_hh, float* __restric
   }
 }
 
-template <int MODE, int H, int C, int BS, int KL, int UPL, int RG>
+template <int MODE, int H, int C, int BS, int KL, int UPL, int RG, bool VL = false>
 __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     rec_bwd_kernel(const RecBwdParams p, const int nslices) {
   using Cfg = RecCfg<MODE, H, C, BS, KL, UPL, RG>;
@@ -341,6 +359,10 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
   const float* extra = p.extra[dir];
   float* dgates = p.dgates[dir];
 
+  int len_b = T;
+  if constexpr (VL) {
+    if (valid) len_b = p.lengths[b];
+  }
   float dh_carry = 0.f, dc_carry = 0.f;
   if (valid) {
     if (p.dh_n) dh_carry = p.dh_n[((size_t)dir * B + b) * H + j];
@@ -382,7 +404,10 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     }
 
     // ---- cell backward for (unit j, batch b) ----------------------------------------------------
-    const float dh = dh_carry + dyv;
+    float dh = dh_carry + dyv;
+    if constexpr (VL) {
+      if (t >= len_b) dh = dh_carry;  // the output of a frozen step is the constant 0: its dy reaches nothing
+    }
     float dg[G], direct, dhn = 0.f;
     if (MODE == B200RNN_GRU) {
       const float r = sv[0], z = sv[1], n = sv[2], hn = sx;
@@ -401,8 +426,22 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
       dg[1] = dc * hp * fg * (1.f - fg);
       dg[2] = dc * ig * (1.f - gg * gg);
       dg[G - 1] = dout;
-      dc_carry = dc * fg;
+      const float dc_next = dc * fg;
       direct = 0.f;
+      if constexpr (VL) {
+        if (t >= len_b) direct = dh;  // frozen step: dh and dc pass straight through
+        else dc_carry = dc_next;
+      } else {
+        dc_carry = dc_next;
+      }
+    }
+    if constexpr (VL) {
+      if (t >= len_b) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) dg[g] = 0.f;
+        dhn = 0.f;
+        if (MODE == B200RNN_GRU) direct = dh;
+      }
     }
     if (valid) {
 #pragma unroll
@@ -557,7 +596,7 @@ template <int MODE, int H, int C, int BS, int KL, int UPL, int RG>
 bool try_fwd(const RecFwdParams& p, cudaStream_t s, bool force, int* rc) {
   using Cfg = RecCfg<MODE, H, C, BS, KL, UPL, RG>;
   static_assert(Cfg::FWD_SMEM <= MAX_SMEM, "forward config does not fit an SM");
-  auto k = rec_fwd_kernel<MODE, H, C, BS, KL, UPL, RG>;
+  auto k = p.lengths ? rec_fwd_kernel<MODE, H, C, BS, KL, UPL, RG, true> : rec_fwd_kernel<MODE, H, C, BS, KL, UPL, RG, false>;
   const int nslices = (p.B + BS - 1) / BS;
   const int nclusters = nslices * p.D;
   static const bool debug = getenv("B200RNN_DEBUG") != nullptr;
@@ -573,7 +612,7 @@ template <int MODE, int H, int C, int BS, int KL, int UPL, int RG>
 bool try_bwd(RecBwdParams& p, cudaStream_t s, bool force, int* rc) {
   using Cfg = RecCfg<MODE, H, C, BS, KL, UPL, RG>;
   static_assert(Cfg::BWD_SMEM <= MAX_SMEM, "backward config does not fit an SM");
-  auto k = rec_bwd_kernel<MODE, H, C, BS, KL, UPL, RG>;
+  auto k = p.lengths ? rec_bwd_kernel<MODE, H, C, BS, KL, UPL, RG, true> : rec_bwd_kernel<MODE, H, C, BS, KL, UPL, RG, false>;
   const int nslices = (p.B + BS - 1) / BS;
   const int nclusters = nslices * p.D;
   if (!force && nclusters > max_active_clusters(k, C, Cfg::NT, Cfg::BWD_SMEM)) return false;

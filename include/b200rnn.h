@@ -124,14 +124,19 @@ B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_
  *                             preparation of the layer-0 input projection); NULL = no LayerNorm
  *   y_pool                  : optional [B, D*H] = sum over time of the top layer's output; with y == NULL the
  *                             [T,B,D*H] output is never written (only allowed without B200RNN_FLAG_SAVE_FOR_BACKWARD)
- * Everything else as b200rnn_forward (which is this call with the four extra arguments zero).
+ *   lengths                 : optional DEVICE array [B] of valid step counts (torch PackedSequence semantics on the
+ *                             padded [T,B,*] layout, DAICFeatureExtarction/feature_extraction.py:45-64 yields such
+ *                             ragged sequences): past its length a sequence keeps its state (h_n / c_n are the state
+ *                             at its last valid step) and its output rows are 0; the reverse direction starts at
+ *                             lengths[b]-1. NULL = every sequence has T steps. Must be passed again to backward.
+ * Everything else as b200rnn_forward (which is this call with the five extra arguments zero).
  */
 B200RNN_API int b200rnn_forward_fused(const b200rnn_desc* desc, const float* x, int64_t x_stride_t,
                                       int64_t x_stride_b, const float* const* params, float* y, int64_t y_stride_t,
                                       int64_t y_stride_b, float* h_n, float* c_n, void* reserve, void* scratch,
                                       uint64_t dropout_seed, uint64_t dropout_offset, uint64_t* rng_state,
                                       const float* ln_gamma, const float* ln_beta, float ln_eps, float* y_pool,
-                                      void* stream /* cudaStream_t */);
+                                      const int32_t* lengths, void* stream /* cudaStream_t */);
 
 /*
  * Backward pass (BPTT): what autograd runs for loss.backward() through nn.GRU / nn.LSTM
@@ -144,13 +149,14 @@ B200RNN_API int b200rnn_forward_fused(const b200rnn_desc* desc, const float* x, 
  *   dparams   4*L*D device pointers shaped like params (e.g. views into ONE flat gradient bucket that
  *             a single ncclAllReduce consumes); entries may be NULL to skip; written or accumulated per
  *             B200RNN_FLAG_ACCUMULATE_GRADS
+ *   lengths   the array given to b200rnn_forward_fused, or NULL
  */
 B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64_t x_stride_t,
                                  int64_t x_stride_b, const float* const* params, const float* y,
                                  int64_t y_stride_t, int64_t y_stride_b, const float* dy, int64_t dy_stride_t,
                                  int64_t dy_stride_b, const float* dh_n, const float* dc_n, const void* reserve,
                                  void* scratch, float* dx, int64_t dx_stride_t, int64_t dx_stride_b,
-                                 float* const* dparams, void* stream /* cudaStream_t */);
+                                 float* const* dparams, const int32_t* lengths, void* stream /* cudaStream_t */);
 
 /*
  * Dense helper used by the path (time-parallel input projection, wgrad, dgrad):

@@ -648,6 +648,8 @@ int launch_rec_fwd(const RecFwdParams& p, cudaStream_t s) {
   int rc = B200RNN_OK;
   if (p.B <= 0 || p.T <= 0) return rc;
   static const int variant = env_variant("B200RNN_FWD_VARIANT");  // tuning knob for the GRU H=256 forward
+  static const int rec_tc = env_variant("B200RNN_REC_TC");
+  if (rec_tc && launch_rec_fwd_tc(p, s, &rc)) return rc;
   if (p.mode == B200RNN_GRU && p.H == 256) {
     if (variant == 1) {
       if (try_fwd<B200RNN_GRU, 256, 4, 4, 32, 8, 1>(p, s, false, &rc)) return rc;

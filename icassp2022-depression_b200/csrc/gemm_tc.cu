@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                        const TcArgs args) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned by offset so that the compiler keeps the shared state space (LDS/STS instead of generic LD/ST)
+  unsigned char* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;   // [2]
@@ -129,7 +130,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][BN] folded bias of the tile, per TMEM set
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // canonical warp index: the shuffle makes it warp-uniform for the compiler, so the single-thread TMA / MMA issue
+  // loops below stay on the uniform datapath (no per-instruction R2UR broadcast loop around UTMALDG / UTCHMMA)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int nkb_total = (args.K + BK - 1) / BK;  // TMA zero-fills the K tail
   const int ntiles = args.tiles_m * args.tiles_n;
   const int nitems = ntiles * args.splitk;
@@ -159,10 +162,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one_sync()) {
       int it = 0;  // running k-block counter across tiles (ring position)
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int tile = item % ntiles, ks = item / ntiles;
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (ptx::elect_one_sync()) {
       int it = 0, ti = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ti) {
         const int nkb = min(nkb_total, (item / ntiles + 1) * args.kb_per_split) - (item / ntiles) * args.kb_per_split;

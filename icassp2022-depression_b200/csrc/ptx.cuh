@@ -40,6 +40,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// one lane of the (fully converged) warp returns true; unlike `lane == 0` the compiler keeps the enclosed code on
+// the uniform datapath (tcgen05.mma / commit operands in uniform registers, no per-instruction broadcast loop)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP) -----------------
 // dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,

@@ -22,19 +22,27 @@
 //     buffered); the RECEIVER splits it into the three MMA operand forms — one third of the DSMEM bytes of sending
 //     the split forms.
 //
-// STATUS (round 1): parity-green (all -m gpu tests pass with B200RNN_REC_TC=1; y error vs torch CPU 7e-7 at
-// B=128, T=120, two layers) but NOT the default: 656 us per GRU layer launch against 231 us for the FFMA kernel.
-// clock64 timeline of one step (profiles/r01_tc_rec_trace.txt, B=128 -> NB=9, C=8), 9 700 cycles:
-//     wait for h slices 510 | split pass + fence + barrier 765 | MMA issue 4 620 | commit -> mbarrier 160 |
-//     tcgen05.ld + smem meet + barrier 580 | cell update + st.async exchange 2 950
-// What that says: (1) with both operands in shared memory an M128 x N16 MMA costs ~58 cycles and ~116 when it
-// depends on the previous one through its accumulator (skipping half of the MMAs changed nothing while they still
-// alternated over the same accumulators) - the weights must live in TMEM (tcgen05.mma with A from tensor memory,
-// 384 of the 512 columns for A_hi + A_lo) and the 80 MMAs must rotate over >= 8 accumulators; (2) an all-to-all of
-// the fp32 state over C = 8 CTAs moves 8 KB per CTA and step through DSMEM, ~3x the FFMA kernel's C = 4 exchange;
-// (3) every phase boundary is a CTA barrier - the phases have to be overlapped across two independent batch groups.
-// That redesign is the round-2 lever; this file is the verified starting point (descriptors, swizzle, both MMA kinds,
-// TMEM epilogue and the exchange protocol are known-good).
+// STATUS (round 1): parity-green (every -m gpu test passes with B200RNN_REC_TC=1; y error vs torch CPU 7e-7 at
+// B=128, T=120, two layers) but opt-in, NOT the default: at the benchmark shape (B=128 per GPU) a GRU layer launch
+// takes 354 us against 231 us for the FFMA kernel; it is ahead only for small batches (GRU H=256, B <= 45:
+// 228-243 us vs 244-254 us per layer forward incl. the input GEMM, tools/rec_crossover.py).
+// clock64 timeline of one step (profiles/r01_tc_rec_trace.txt), B=128 -> NB=9 rows per cluster of 8 CTAs:
+//     4 350 cycles = wait for h 90-140 | split pass + proxy fence + barrier 660-700 | MMA issue 1 300 (80 MMAs,
+//     16 cycles each, A from TMEM) | commit -> mbarrier 100-170 | tcgen05.ld + smem meet + barrier 265 |
+//     cell update + st.async exchange 1 850-3 500
+// and 3 020 cycles at B=16 (NB=2: exchange 680). What was learned on the way (all measured):
+//   (1) a tcgen05.mma issued under `if (tid == 0)` is wrapped by the compiler in an ELECT / R2UR.BROADCAST /
+//       BRA.U.ANY loop (operands are not provably warp-uniform): ~55 cycles per MMA, 4 620 per step. Issuing from
+//       `if (warp_uniform == 0) if (elect_one_sync())` keeps operands in uniform registers: 16 cycles per MMA.
+//       The same fix in gemm_tc.cu took the BiLSTM H=256 train step from 1.35 to 1.09 ms.
+//   (2) with A in shared memory an M128xN16 MMA has to read 4 KB of A: the weights belong in TMEM (done: A_hi).
+//   (3) a pointer rounded up through uintptr_t loses its shared state space: the loads become generic LD and queue
+//       behind the outstanding global prefetches (~900 cycles per batch row). Align by offset instead.
+//   (4) what binds now is DSMEM bandwidth: all-to-all of the fp32 state over C = 8 CTAs is 7 x NB x 128 B out and
+//       as much in per CTA and step; at the measured ~17 B/cycle (both directions together) that is ~1 100 cycles
+//       for NB = 9, against ~360 for the FFMA kernel's C = 4 / 4-row clusters. C = 8 is forced by the operand
+//       bytes (A_hi + A_lo = 6 B per weight). A win at B = 128 needs the exchange hidden behind the MMAs of a second
+//       batch group, or fewer bytes per weight so that C = 4 fits - the round-2 lever.
 #include <cuda_bf16.h>
 #include <mutex>
 #include <stdlib.h>
@@ -62,16 +70,19 @@ struct TcCfg {
   static constexpr int NKB2 = H / 64;              // bf16 K-blocks (64 bf16)
   static constexpr int A_KB = MR * 128;            // bytes per K-block of A
   static constexpr int B_KB = NBMAX * 128;         // bytes per K-block of B
-  static constexpr int OFF_AHI = 0;
-  static constexpr int OFF_ALO = OFF_AHI + NKB * A_KB;
-  static constexpr int OFF_BHI = OFF_ALO + NKB2 * A_KB;
+  static constexpr int OFF_ALO = 0;                                // A_hi lives in TMEM, A_lo (bf16) in shared memory
+  static constexpr int OFF_BHI = OFF_ALO + NKB2 * A_KB + 4096;     // +4 KB: the M=128 MMA reads 32 rows past MR
   static constexpr int OFF_BLO = OFF_BHI + NKB * B_KB;
   static constexpr int OFF_BBF = OFF_BLO + NKB * B_KB;
   static constexpr int OFF_RECV = OFF_BBF + NKB2 * B_KB;           // [2][NBMAX][H] fp32
   static constexpr int OFF_PRE = OFF_RECV + 2 * NBMAX * H * 4;     // [G][NBMAX][32] fp32
   static constexpr int OFF_BAR = OFF_PRE + G * NBMAX * UCTA * 4;   // recv[2], mma, tmem slot
-  static constexpr int SMEM = OFF_BAR + 64 + 1024 /*alignment slack*/;
+  static constexpr int SMEM = OFF_BAR + 256 + 1024 /*alignment slack*/;
   static_assert(SMEM <= TC_MAX_SMEM, "tensor-core recurrence does not fit an SM for this shape");
+  static constexpr int COL_AHI = 0;                                // TMEM columns [0, H): A_hi, lane = gate row
+  static constexpr int COL_ACC = 384;                              // 8 accumulators of NBMAX columns
+  static constexpr int NACC = 8;
+  static_assert(H <= COL_ACC, "A_hi must leave room for the accumulators");
   static_assert(OFF_ALO % 1024 == 0 && OFF_BHI % 1024 == 0 && OFF_BLO % 1024 == 0 && OFF_BBF % 1024 == 0 &&
                     A_KB % 1024 == 0,
                 "swizzle atoms must stay 1024-byte aligned");
@@ -94,6 +105,26 @@ __device__ __forceinline__ void tcr_mma_tf32(uint32_t tmem_d, uint64_t adesc, ui
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// A from tensor memory (lane = row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void tcr_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tcr_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void tcr_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -156,19 +187,23 @@ __global__ void __launch_bounds__(TC_NT, 1) rec_fwd_tc_kernel(const RecFwdParams
   using Cfg = TcCfg<MODE, H>;
   constexpr int G = Cfg::G, C = Cfg::C, MR = Cfg::MR, GH = G * H;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* base =
-      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* a_hi = base + Cfg::OFF_AHI;
+  // 1024-byte alignment by OFFSET (not by integer round-trip of the pointer): the compiler keeps the shared state
+  // space, so the accesses below are LDS/STS. Generic loads would queue behind the outstanding global prefetches.
+  unsigned char* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* a_lo = base + Cfg::OFF_ALO;
   unsigned char* b_hi = base + Cfg::OFF_BHI;
   unsigned char* b_lo = base + Cfg::OFF_BLO;
   unsigned char* b_bf = base + Cfg::OFF_BBF;
   float* recv = reinterpret_cast<float*>(base + Cfg::OFF_RECV);  // [2][NBMAX][H]
   float* pre = reinterpret_cast<float*>(base + Cfg::OFF_PRE);    // [G][NBMAX][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + Cfg::OFF_BAR);  // [0],[1] state buffers, [2] MMA done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  // [buf*8 + src]: slice of h from CTA `src` has landed in recv[buf] (one barrier per source: 72 st.async
+  // completions each instead of 576 on one word); [16]: the step's MMAs are done
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + Cfg::OFF_BAR);
+  uint64_t* mma_bar = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(FULLMASK, tid >> 5, 0);  // warp-uniform by construction
   const uint32_t rank = ptx::cluster_ctarank();
   const int cid = blockIdx.x / C;
   const int dir = cid / nslices;
@@ -179,44 +214,61 @@ __global__ void __launch_bounds__(TC_NT, 1) rec_fwd_tc_kernel(const RecFwdParams
   const float* w_hh = p.w_hh[dir];
 
   if (tid == 0) {
-    ptx::mbar_init(&bars[0], 1);
-    ptx::mbar_init(&bars[1], 1);
-    ptx::mbar_init(&bars[2], 1);
+    for (int i = 0; i < 17; ++i) ptx::mbar_init(&bars[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(tmem_slot)),
-                 "r"(64u)
+                 "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  tcr_fence_before();
+  __syncthreads();
+  tcr_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
 
-  // ---- W_hh rows of this CTA -> A_hi (tf32) / A_lo (bf16 of the remainder), swizzled K-major ------------------
+  // ---- W_hh rows of this CTA: A_hi = tf32(W) -> tensor memory (thread = lane = gate row m, column = k) --------
+  {
+    const int m = tid, g = m / UCTA, uu = m - g * UCTA;
+    const float* wrow = w_hh + ((size_t)(m < MR ? g : 0) * H + j0 + uu) * H;
+    const uint32_t trow_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)Cfg::COL_AHI;
+    for (int k0 = 0; k0 < H; k0 += 16) {
+      uint32_t r[16];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(wrow + k0 + 4 * v));
+        r[4 * v + 0] = (m < MR) ? to_tf32(x.x) : 0u;
+        r[4 * v + 1] = (m < MR) ? to_tf32(x.y) : 0u;
+        r[4 * v + 2] = (m < MR) ? to_tf32(x.z) : 0u;
+        r[4 * v + 3] = (m < MR) ? to_tf32(x.w) : 0u;
+      }
+      tcr_st_x16(trow_addr + (uint32_t)k0, r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  // ---- A_lo = bf16(W - A_hi) -> shared memory, swizzled K-major ------------------------------------------------
   for (int i = tid; i < MR * (H / 4); i += TC_NT) {
     const int m = i / (H / 4), k = (i - m * (H / 4)) * 4;
-    const int g = m / UCTA, u = m - g * UCTA;
-    const float4 x = __ldg(reinterpret_cast<const float4*>(w_hh + ((size_t)g * H + j0 + u) * H + k));
-    uint4 hi;
-    hi.x = to_tf32(x.x); hi.y = to_tf32(x.y); hi.z = to_tf32(x.z); hi.w = to_tf32(x.w);
-    const int kb = k >> 5, c = (k & 31) >> 2;
-    *reinterpret_cast<uint4*>(a_hi + kb * Cfg::A_KB + sw128(m, c)) = hi;
-    const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - __uint_as_float(hi.x), x.y - __uint_as_float(hi.y));
-    const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - __uint_as_float(hi.z), x.w - __uint_as_float(hi.w));
+    const int g = m / UCTA, uu = m - g * UCTA;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(w_hh + ((size_t)g * H + j0 + uu) * H + k));
+    const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - __uint_as_float(to_tf32(x.x)), x.y - __uint_as_float(to_tf32(x.y)));
+    const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - __uint_as_float(to_tf32(x.z)), x.w - __uint_as_float(to_tf32(x.w)));
     uint2 lo;
     lo.x = *reinterpret_cast<const uint32_t*>(&l01);
     lo.y = *reinterpret_cast<const uint32_t*>(&l23);
     const int kb2 = k >> 6, c2 = (k & 63) >> 3, half = (k >> 2) & 1;
     *reinterpret_cast<uint2*>(a_lo + kb2 * Cfg::A_KB + sw128(m, c2) + half * 8) = lo;
   }
-  // operand rows >= NB are never written by the split pass: keep them finite
-  for (int i = tid; i < (Cfg::OFF_RECV - Cfg::OFF_BHI) / 16; i += TC_NT)
-    reinterpret_cast<uint4*>(b_hi)[i] = make_uint4(0, 0, 0, 0);
+  // operand rows >= NB are never written by the split pass, and the M=128 MMA reads 32 rows past A_lo: keep finite
+  for (int i = tid; i < (Cfg::OFF_RECV - Cfg::NKB2 * Cfg::A_KB) / 16; i += TC_NT)
+    reinterpret_cast<uint4*>(a_lo + Cfg::NKB2 * Cfg::A_KB)[i] = make_uint4(0, 0, 0, 0);
   ptx::fence_proxy_async();
   tcr_fence_before();
   __syncthreads();
   tcr_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (tid == 0 && T > 1) ptx::mbar_arrive_expect_tx(&bars[1], (uint32_t)(NB * H * sizeof(float)));
+  if (tid == 0 && T > 1)
+    for (int src = 0; src < C; ++src) ptx::mbar_arrive_expect_tx(&bars[8 + src], (uint32_t)(NB * UCTA * sizeof(float)));
   ptx::cluster_sync_all();  // peers' barriers are initialised before anyone stores into them
 
   // ---- thread identity for the cell update: unit u, batch rows n = q + 4 i ------------------------------------
@@ -240,7 +292,7 @@ __global__ void __launch_bounds__(TC_NT, 1) rec_fwd_tc_kernel(const RecFwdParams
     }
   }
 
-  const uint64_t d_ahi = tcr_desc(ptx::smem_u32(a_hi)), d_alo = tcr_desc(ptx::smem_u32(a_lo));
+  const uint64_t d_alo = tcr_desc(ptx::smem_u32(a_lo));
   const uint64_t d_bhi = tcr_desc(ptx::smem_u32(b_hi)), d_blo = tcr_desc(ptx::smem_u32(b_lo));
   const uint64_t d_bbf = tcr_desc(ptx::smem_u32(b_bf));
 
@@ -257,141 +309,189 @@ __global__ void __launch_bounds__(TC_NT, 1) rec_fwd_tc_kernel(const RecFwdParams
 
     if (step > 0) {
       // ---- h_step has arrived from every CTA of the cluster: split it into the MMA operand forms --------------
-      tcr_wait(&bars[cur], (uint32_t)(((step - 1) >> 1) & 1));
+      // warp w converts the K-blocks (= source CTAs) [w*KPW, w*KPW + KPW) of all NB rows and waits only for those
+      constexpr int KPW = C / 4;
+      const uint32_t par = (uint32_t)(((step - 1) >> 1) & 1);
+#pragma unroll
+      for (int s2 = 0; s2 < KPW; ++s2) tcr_wait(&bars[cur * 8 + warp * KPW + s2], par);
       if (tr) trow[1] = clock64();
       const float* hc = recv + cur * NBMAX * H;
-      for (int i = tid; i < NB * (H / 4); i += TC_NT) {
-        const int n = i / (H / 4), k = (i - n * (H / 4)) * 4;
-        const float4 x = *reinterpret_cast<const float4*>(hc + n * H + k);
-        uint4 hi;
-        hi.x = to_tf32(x.x); hi.y = to_tf32(x.y); hi.z = to_tf32(x.z); hi.w = to_tf32(x.w);
-        float4 lo;
-        lo.x = x.x - __uint_as_float(hi.x); lo.y = x.y - __uint_as_float(hi.y);
-        lo.z = x.z - __uint_as_float(hi.z); lo.w = x.w - __uint_as_float(hi.w);
-        const int kb = k >> 5, c = (k & 31) >> 2;
-        const uint32_t o = (uint32_t)(kb * Cfg::B_KB) + sw128(n, c);
-        *reinterpret_cast<uint4*>(b_hi + o) = hi;
-        *reinterpret_cast<float4*>(b_lo + o) = lo;
-        const __nv_bfloat162 v01 = __floats2bfloat162_rn(x.x, x.y), v23 = __floats2bfloat162_rn(x.z, x.w);
-        uint2 bf;
-        bf.x = *reinterpret_cast<const uint32_t*>(&v01);
-        bf.y = *reinterpret_cast<const uint32_t*>(&v23);
-        const int kb2 = k >> 6, c2 = (k & 63) >> 3, half = (k >> 2) & 1;
-        *reinterpret_cast<uint2*>(b_bf + kb2 * Cfg::B_KB + sw128(n, c2) + half * 8) = bf;
+      const int total = NB * KPW * 8;  // 16-byte chunks this warp converts
+#pragma unroll 1
+      for (int i0 = 0; i0 < total; i0 += 4 * 32) {
+        float4 xv[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int i = i0 + v * 32 + lane;
+          const int n = i / (KPW * 8), k = (warp * KPW * 8 + (i - n * (KPW * 8))) * 4;
+          xv[v] = (i < total) ? *reinterpret_cast<const float4*>(hc + n * H + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int i = i0 + v * 32 + lane;
+          if (i < total) {
+            const float4 x = xv[v];
+            const int n = i / (KPW * 8), k = (warp * KPW * 8 + (i - n * (KPW * 8))) * 4;
+            uint4 hi;
+            hi.x = to_tf32(x.x); hi.y = to_tf32(x.y); hi.z = to_tf32(x.z); hi.w = to_tf32(x.w);
+            float4 lo;
+            lo.x = x.x - __uint_as_float(hi.x); lo.y = x.y - __uint_as_float(hi.y);
+            lo.z = x.z - __uint_as_float(hi.z); lo.w = x.w - __uint_as_float(hi.w);
+            const int kb = k >> 5, c = (k & 31) >> 2;
+            const uint32_t o = (uint32_t)(kb * Cfg::B_KB) + sw128(n, c);
+            *reinterpret_cast<uint4*>(b_hi + o) = hi;
+            *reinterpret_cast<float4*>(b_lo + o) = lo;
+            const __nv_bfloat162 v01 = __floats2bfloat162_rn(x.x, x.y), v23 = __floats2bfloat162_rn(x.z, x.w);
+            uint2 bf;
+            bf.x = *reinterpret_cast<const uint32_t*>(&v01);
+            bf.y = *reinterpret_cast<const uint32_t*>(&v23);
+            const int kb2 = k >> 6, c2 = (k & 63) >> 3, half = (k >> 2) & 1;
+            *reinterpret_cast<uint2*>(b_bf + kb2 * Cfg::B_KB + sw128(n, c2) + half * 8) = bf;
+          }
+        }
       }
       ptx::fence_proxy_async();
       tcr_fence_before();
       __syncthreads();
       if (tr) trow[2] = clock64();
-      if (tid == 0) {
+      if (warp == 0) {
+       const uint32_t tmem_u = __shfl_sync(FULLMASK, tmem_base, 0);
+       if (ptx::elect_one_sync()) {
         tcr_fence_after();
+        // 5 * NKB/2 MMAs rotate over NACC accumulators so that none waits for its predecessor's accumulate
+        int jm = 0;
 #pragma unroll
         for (int kb = 0; kb < Cfg::NKB; ++kb) {
-          const uint32_t acc_main = tmem_base + (uint32_t)((kb % 3) * NBMAX);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t a = d_ahi + (uint64_t)((kb * Cfg::A_KB + k * 32) >> 4);
+            const uint32_t a = tmem_u + (uint32_t)(Cfg::COL_AHI + kb * 32 + k * 8);
             const uint64_t bh = d_bhi + (uint64_t)((kb * Cfg::B_KB + k * 32) >> 4);
             const uint64_t bl = d_blo + (uint64_t)((kb * Cfg::B_KB + k * 32) >> 4);
-            tcr_mma_tf32(acc_main, a, bh, IDESC_TF32, (kb >= 3 || k != 0) ? 1u : 0u);
-            tcr_mma_tf32(tmem_base + 3 * NBMAX, a, bl, IDESC_TF32, (kb | k) != 0 ? 1u : 0u);
+            tcr_mma_tf32_ts(tmem_u + (uint32_t)(Cfg::COL_ACC + (jm % Cfg::NACC) * NBMAX), a, bh, IDESC_TF32,
+                            jm >= Cfg::NACC ? 1u : 0u);
+            ++jm;
+            tcr_mma_tf32_ts(tmem_u + (uint32_t)(Cfg::COL_ACC + (jm % Cfg::NACC) * NBMAX), a, bl, IDESC_TF32,
+                            jm >= Cfg::NACC ? 1u : 0u);
+            ++jm;
+            if (((kb * 4 + k) & 1) == 1) {
+              const int i2 = (kb * 4 + k) >> 1, kb2 = i2 >> 2, kk = i2 & 3;
+              tcr_mma_bf16(tmem_u + (uint32_t)(Cfg::COL_ACC + (jm % Cfg::NACC) * NBMAX),
+                           d_alo + (uint64_t)((kb2 * Cfg::A_KB + kk * 32) >> 4),
+                           d_bbf + (uint64_t)((kb2 * Cfg::B_KB + kk * 32) >> 4), IDESC_BF16, jm >= Cfg::NACC ? 1u : 0u);
+              ++jm;
+            }
           }
         }
-#pragma unroll
-        for (int kb2 = 0; kb2 < Cfg::NKB2; ++kb2)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tcr_mma_bf16(tmem_base + 3 * NBMAX, d_alo + (uint64_t)((kb2 * Cfg::A_KB + k * 32) >> 4),
-                         d_bbf + (uint64_t)((kb2 * Cfg::B_KB + k * 32) >> 4), IDESC_BF16, 1u);
-        tcr_commit(&bars[2]);
-        if (tr) trow[3] = clock64();
+        tcr_commit(mma_bar);
+       }
+       __syncwarp();
+       if (tr) trow[3] = clock64();
       }
-      __syncwarp();
     }
     // h_step is consumed (copied into the operand buffers): re-arm the other buffer for h_{step+1}... which is
     // bars[nxt]; for step 0 that was done before the loop
-    if (tid == 0 && step > 0 && step + 1 < T) ptx::mbar_arrive_expect_tx(&bars[nxt], (uint32_t)(NB * H * sizeof(float)));
+    if (tid == 0 && step > 0 && step + 1 < T)
+      for (int src = 0; src < C; ++src)
+        ptx::mbar_arrive_expect_tx(&bars[nxt * 8 + src], (uint32_t)(NB * UCTA * sizeof(float)));
 
     if (step > 0) {
-      tcr_wait(&bars[2], (uint32_t)((step - 1) & 1));
+      tcr_wait(mma_bar, (uint32_t)((step - 1) & 1));
       tcr_fence_after();
       if (tr) trow[4] = clock64();
       if (warp < G) {
         const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
         uint32_t r0[16], r1[16], r2[16], r3[16];
-        tcr_ld_x16(lane_base + 0 * NBMAX, r0);
-        tcr_ld_x16(lane_base + 1 * NBMAX, r1);
-        tcr_ld_x16(lane_base + 2 * NBMAX, r2);
-        tcr_ld_x16(lane_base + 3 * NBMAX, r3);
+        float sum[NBMAX];
+        tcr_ld_x16(lane_base + (uint32_t)(Cfg::COL_ACC + 0 * NBMAX), r0);
+        tcr_ld_x16(lane_base + (uint32_t)(Cfg::COL_ACC + 1 * NBMAX), r1);
+        tcr_ld_x16(lane_base + (uint32_t)(Cfg::COL_ACC + 2 * NBMAX), r2);
+        tcr_ld_x16(lane_base + (uint32_t)(Cfg::COL_ACC + 3 * NBMAX), r3);
+        tcr_wait_ld();
+#pragma unroll
+        for (int n = 0; n < NBMAX; ++n)
+          sum[n] = (__uint_as_float(r0[n]) + __uint_as_float(r1[n])) + (__uint_as_float(r2[n]) + __uint_as_float(r3[n]));
+        tcr_ld_x16(lane_base + (uint32_t)(Cfg::COL_ACC + 4 * NBMAX), r0);
+        tcr_ld_x16(lane_base + (uint32_t)(Cfg::COL_ACC + 5 * NBMAX), r1);
+        tcr_ld_x16(lane_base + (uint32_t)(Cfg::COL_ACC + 6 * NBMAX), r2);
+        tcr_ld_x16(lane_base + (uint32_t)(Cfg::COL_ACC + 7 * NBMAX), r3);
         tcr_wait_ld();
         float* dst = pre + (size_t)warp * NBMAX * UCTA + lane;
 #pragma unroll
         for (int n = 0; n < NBMAX; ++n)
           if (n < NB)
-            dst[n * UCTA] = (__uint_as_float(r0[n]) + __uint_as_float(r1[n])) +
-                            (__uint_as_float(r2[n]) + __uint_as_float(r3[n]));
+            dst[n * UCTA] = sum[n] + ((__uint_as_float(r0[n]) + __uint_as_float(r1[n])) +
+                                      (__uint_as_float(r2[n]) + __uint_as_float(r3[n])));
       }
       tcr_fence_before();
       __syncthreads();
       if (tr) trow[5] = clock64();
     }
 
-    // ---- cell update for (unit u, rows q, q+4, ...) ------------------------------------------------------------
+    // ---- cell update for (unit u, rows q, q+4, ...): all rows' math first, then the exchange, then global traffic --
+    float hnew[4], sv[4][4], sx[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int n = q + 4 * i;
+      hnew[i] = 0.f;
       if (n >= NB) break;
-      const int b = b0 + n;
-      const bool valid = b < B;
       float a[G];
 #pragma unroll
       for (int g = 0; g < G; ++g) a[g] = (step > 0) ? pre[((size_t)g * NBMAX + n) * UCTA + u] : 0.f;
-      float hnew, s0, s1, s2, s3 = 0.f, sx;
       if (MODE == B200RNN_GRU) {
         const float r = sigm(gi[i][0] + a[0]);
         const float z = sigm(gi[i][1] + a[1]);
         const float hn = a[2] + bhn;
         const float nn = tanh_f(gi[i][2] + r * hn);
-        hnew = nn + z * (h_prev[i] - nn);
-        s0 = r; s1 = z; s2 = nn; sx = hn;
+        hnew[i] = nn + z * (h_prev[i] - nn);
+        sv[i][0] = r; sv[i][1] = z; sv[i][2] = nn; sv[i][3] = 0.f; sx[i] = hn;
       } else {
         const float ig = sigm(gi[i][0] + a[0]);
         const float fg = sigm(gi[i][1] + a[1]);
         const float gg = tanh_f(gi[i][2] + a[2]);
         const float og = sigm(gi[i][G - 1] + a[G - 1]);
         const float cnew = fg * c_prev[i] + ig * gg;
-        hnew = og * tanh_f(cnew);
+        hnew[i] = og * tanh_f(cnew);
         c_prev[i] = cnew;
-        s0 = ig; s1 = fg; s2 = gg; s3 = og; sx = cnew;
+        sv[i][0] = ig; sv[i][1] = fg; sv[i][2] = gg; sv[i][3] = og; sx[i] = cnew;
       }
-      h_prev[i] = hnew;
-      h_sum[i] += hnew;
-
-      if (step + 1 < T) {
+      h_prev[i] = hnew[i];
+      h_sum[i] += hnew[i];
+    }
+    if (step + 1 < T) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = q + 4 * i;
+        if (n >= NB) break;
         // 4 consecutive units -> one 16-byte st.async per destination CTA; lane&3 picks the destinations
         float4 v;
-        v.x = __shfl_sync(FULLMASK, hnew, (lane & ~3) + 0);
-        v.y = __shfl_sync(FULLMASK, hnew, (lane & ~3) + 1);
-        v.z = __shfl_sync(FULLMASK, hnew, (lane & ~3) + 2);
-        v.w = __shfl_sync(FULLMASK, hnew, (lane & ~3) + 3);
+        v.x = __shfl_sync(FULLMASK, hnew[i], (lane & ~3) + 0);
+        v.y = __shfl_sync(FULLMASK, hnew[i], (lane & ~3) + 1);
+        v.z = __shfl_sync(FULLMASK, hnew[i], (lane & ~3) + 2);
+        v.w = __shfl_sync(FULLMASK, hnew[i], (lane & ~3) + 3);
         const uint32_t dst = ptx::smem_u32(recv + (size_t)nxt * NBMAX * H + n * H + j0 + (lane & ~3));
-        const uint32_t bar = ptx::smem_u32(&bars[nxt]);
+        const uint32_t bar = ptx::smem_u32(&bars[nxt * 8 + (int)rank]);
 #pragma unroll
-        for (int r = (lane & 3); r < C; r += 4) ptx::st_async_v4(ptx::mapa(dst, (uint32_t)r), v, ptx::mapa(bar, (uint32_t)r));
+        for (int r = (lane & 3); r < C; r += 4)
+          ptx::st_async_v4(ptx::mapa(dst, (uint32_t)r), v, ptx::mapa(bar, (uint32_t)r));
       }
-
-      if (valid) {
-        if (p.y) p.y[(long long)t * p.y_st + (long long)b * p.y_sb + dir * H + j] = hnew;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = q + 4 * i;
+      if (n >= NB) break;
+      const int b = b0 + n;
+      if (b < B) {
+        if (p.y) p.y[(long long)t * p.y_st + (long long)b * p.y_sb + dir * H + j] = hnew[i];
         if (p.training) {
           float* gp = gates + ((size_t)t * B + b) * GH + j;
-          gp[0] = s0;
-          gp[H] = s1;
-          gp[2 * H] = s2;
-          if (G == 4) gp[3 * H] = s3;
-          extra[((size_t)t * B + b) * H + j] = sx;
+          gp[0] = sv[i][0];
+          gp[H] = sv[i][1];
+          gp[2 * H] = sv[i][2];
+          if (G == 4) gp[3 * H] = sv[i][3];
+          extra[((size_t)t * B + b) * H + j] = sx[i];
         }
         if (step == T - 1) {
-          p.h_n[((size_t)dir * B + b) * H + j] = hnew;
+          p.h_n[((size_t)dir * B + b) * H + j] = hnew[i];
           if (p.y_pool) p.y_pool[(size_t)b * p.D * H + dir * H + j] = h_sum[i];
           if (MODE == B200RNN_LSTM && p.c_n) p.c_n[((size_t)dir * B + b) * H + j] = c_prev[i];
         }
@@ -409,7 +509,7 @@ __global__ void __launch_bounds__(TC_NT, 1) rec_fwd_tc_kernel(const RecFwdParams
   __syncthreads();
   if (warp == 0) {
     tcr_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
   ptx::cluster_sync_all();  // nobody exits while a peer could still address its shared memory
 }

@@ -566,7 +566,9 @@ def run_ours(args) -> None:
         # ---- secondary module configs (fwd+bwd ms/batch) and the end-to-end fine-tune variant -----------
         _log(f"roofline pass: rec launch {t_launch * 1e3:.3f} ms x{rec_n}")
         extra = {}
-        if not args.quick:
+        # single-process only: this block runs on rank 0 alone, and the fine-tune variant all-reduces its gradient
+        # bucket - entered by one rank of several it would wait for peers that are already at the final barrier
+        if not args.quick and world == 1:
             extra["c2_audio_gru_whole_train_B64_T120"] = _time_module_train("c2", dev)
             extra["c3_text_bilstm_whole_train_B64_T30_H256"] = _time_module_train("c3", dev)
             extra["c4_finetune_all_grads_B128"] = _finetune_variant(dev)

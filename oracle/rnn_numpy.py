@@ -21,6 +21,13 @@ unpinned" by the reference itself); this restatement is pinned instead against t
 oracle/ref_models.py, against outputs of the reference's own classes recorded in tests/golden/.
 
 Inter-layer dropout is not modelled (compare in eval() / dropout=0).
+
+Ragged batches (``lengths``): PackedSequence semantics of the same modules (packed branch of GRU.forward /
+LSTM.forward, rnn.py:1393-1394,1459-1470 / :1095-1096,1195-1206, fed by torch.nn.utils.rnn.pack_padded_sequence) on the
+padded [T,B,*] block: sequence b takes lengths[b] steps (the reverse direction starts at lengths[b]-1), keeps its state
+afterwards - so h_n / c_n are its state at its last valid step - and its padded output rows are 0. The reference
+pads instead of packing (DAICFeatureExtarction/feature_extraction.py:45-64 produces the ragged sequences); pinned
+against stock torch on packed inputs in tests/test_oracle.py.
 """
 from __future__ import annotations
 
@@ -41,9 +48,10 @@ def _gates(mode: str) -> int:
     raise ValueError(mode)
 
 
-def _layer_forward(mode: str, x: np.ndarray, w_ih, w_hh, b_ih, b_hh, reverse: bool):
+def _layer_forward(mode: str, x: np.ndarray, w_ih, w_hh, b_ih, b_hh, reverse: bool, lengths=None):
     """One layer, one direction. x [T,B,I] -> y [T,B,H], final h (and c), cache for backward."""
     T, B, _ = x.shape
+    live = None if lengths is None else (np.arange(T)[:, None] < np.asarray(lengths)[None, :])  # [T,B]
     H = w_hh.shape[1]
     h = np.zeros((B, H), dtype=x.dtype)
     c = np.zeros((B, H), dtype=x.dtype)
@@ -69,15 +77,22 @@ def _layer_forward(mode: str, x: np.ndarray, w_ih, w_hh, b_ih, b_hh, reverse: bo
             c_new = f * c + i * g
             h_new = o * np.tanh(c_new)
             cache[t] = dict(i=i, f=f, g=g, o=o, c=c_new, c_prev=c, h_prev=h)
+            if live is not None:
+                c_new = np.where(live[t][:, None], c_new, c)
             c = c_new
-        h = h_new
-        y[t] = h
+        if live is not None:
+            y[t] = np.where(live[t][:, None], h_new, 0.0)
+            h = np.where(live[t][:, None], h_new, h)
+        else:
+            h = h_new
+            y[t] = h
     return y, h, c, cache
 
 
-def _layer_backward(mode: str, x, w_ih, w_hh, cache, dy, dh_last, dc_last, reverse: bool):
+def _layer_backward(mode: str, x, w_ih, w_hh, cache, dy, dh_last, dc_last, reverse: bool, lengths=None):
     """BPTT of one layer/direction. Returns dx, dw_ih, dw_hh, db_ih, db_hh."""
     T, B, _ = x.shape
+    live = None if lengths is None else (np.arange(T)[:, None] < np.asarray(lengths)[None, :])  # [T,B]
     H = w_hh.shape[1]
     dx = np.zeros_like(x)
     dw_ih = np.zeros_like(w_ih)
@@ -89,7 +104,8 @@ def _layer_backward(mode: str, x, w_ih, w_hh, cache, dy, dh_last, dc_last, rever
     order = range(T) if reverse else range(T - 1, -1, -1)  # reverse of the forward scan
     for t in order:
         k = cache[t]
-        dht = dh + dy[t]
+        m = None if live is None else live[t][:, None]
+        dht = dh + (dy[t] if m is None else np.where(m, dy[t], 0.0))  # a padded output row is the constant 0
         if mode == "gru":
             r, z, n, hn, h_prev = k["r"], k["z"], k["n"], k["hn"], k["h_prev"]
             dn = dht * (1.0 - z) * (1.0 - n * n)
@@ -97,7 +113,11 @@ def _layer_backward(mode: str, x, w_ih, w_hh, cache, dy, dh_last, dc_last, rever
             dr = dn * hn * r * (1.0 - r)
             dgi = np.concatenate([dr, dz, dn], axis=1)
             dgh = np.concatenate([dr, dz, dn * r], axis=1)
-            dh = dht * z + dgh @ w_hh
+            if m is not None:  # frozen step: no gate gradient, dh passes straight through
+                dgi, dgh = dgi * m, dgh * m
+                dh = np.where(m, dht * z, dht) + dgh @ w_hh
+            else:
+                dh = dht * z + dgh @ w_hh
         else:
             i, f, g, o, c, c_prev, h_prev = k["i"], k["f"], k["g"], k["o"], k["c"], k["c_prev"], k["h_prev"]
             tc = np.tanh(c)
@@ -107,9 +127,14 @@ def _layer_backward(mode: str, x, w_ih, w_hh, cache, dy, dh_last, dc_last, rever
             df = dct * c_prev * f * (1.0 - f)
             dg = dct * i * (1.0 - g * g)
             dgi = np.concatenate([di, df, dg, do], axis=1)
+            if m is not None:  # frozen step: dh and dc pass straight through
+                dgi = dgi * m
+                dc = np.where(m, dct * f, dc)
+                dh = np.where(m, 0.0, dht) + dgi @ w_hh
+            else:
+                dc = dct * f
+                dh = dgi @ w_hh
             dgh = dgi
-            dc = dct * f
-            dh = dgh @ w_hh
         dx[t] = dgi @ w_ih
         dw_ih += dgi.T @ x[t]
         dw_hh += dgh.T @ h_prev
@@ -135,15 +160,18 @@ class NumpyRNN:
         base = 4 * (l * self.D + d)
         return self.w[base:base + 4]
 
-    def forward(self, x: np.ndarray):
+    def forward(self, x: np.ndarray, lengths=None):
+        """x [T,B,I] (padded); ``lengths`` [B] = valid steps per sequence (PackedSequence semantics) or None."""
         x = np.asarray(x, dtype=self.dtype)
+        self._lengths = None if lengths is None else np.asarray(lengths, dtype=np.int64)
         inp = x
         h_n, c_n, saved = [], [], []
         for l in range(self.L):
             outs, caches = [], []
             for d in range(self.D):
                 w_ih, w_hh, b_ih, b_hh = self._p(l, d)
-                y, h, c, cache = _layer_forward(self.mode, inp, w_ih, w_hh, b_ih, b_hh, reverse=(d == 1))
+                y, h, c, cache = _layer_forward(self.mode, inp, w_ih, w_hh, b_ih, b_hh, reverse=(d == 1),
+                                                lengths=self._lengths)
                 outs.append(y)
                 caches.append(cache)
                 h_n.append(h)
@@ -173,7 +201,8 @@ class NumpyRNN:
                 dc_last = np.zeros((B, H), self.dtype) if dc_n is None else np.asarray(dc_n[idx], self.dtype)
                 dyd = dy[:, :, d * H:(d + 1) * H]
                 dx, dw_ih, dw_hh, db_ih, db_hh = _layer_backward(self.mode, inp, w_ih, w_hh, caches[d], dyd,
-                                                                 dh_last, dc_last, reverse=(d == 1))
+                                                                 dh_last, dc_last, reverse=(d == 1),
+                                                                 lengths=self._lengths)
                 dinp += dx
                 grads[(l, d)] = (dw_ih, dw_hh, db_ih, db_hh)
             dy = dinp

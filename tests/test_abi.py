@@ -56,3 +56,49 @@ def test_forward_rejects_null_pointers_before_touching_the_device():
     d = _lib.Desc(_lib.GRU, 2, 2, 16, 128, 1, 1, 0, 0.0, 0)
     rc = lib.b200rnn_forward(ctypes.byref(d), None, 0, 0, None, None, 0, 0, None, None, None, None, 0, 0, None, None)
     assert rc == -1 and b"null pointer" in lib.b200rnn_last_error()
+
+
+def _prototypes():
+    """{name: [C parameter type strings]} parsed from include/b200rnn.h (comments stripped)."""
+    text = open(os.path.join(ROOT, "include", "b200rnn.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    out = {}
+    for m in re.finditer(r"B200RNN_API\s+[\w\s\*]+?\b(b200rnn_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        out[m.group(1)] = [] if params in ([""], ["void"]) else params
+    return out
+
+
+def _kind_of_c(param: str) -> str:
+    if "*" in param:
+        return "ptr"
+    for c_name, kind in (("uint64_t", "u64"), ("int64_t", "i64"), ("uint32_t", "u32"), ("size_t", "size"),
+                         ("float", "f32"), ("int32_t", "i32"), ("int", "i32")):
+        if re.search(rf"\b{c_name}\b", param):
+            return kind
+    raise AssertionError(f"unclassified C parameter: {param!r}")
+
+
+def _kind_of_ctypes(t) -> str:
+    if t is ctypes.c_void_p or t is ctypes.c_char_p or hasattr(t, "contents"):
+        return "ptr"
+    return {ctypes.c_uint64: "u64", ctypes.c_int64: "i64", ctypes.c_uint32: "u32", ctypes.c_size_t: "size",
+            ctypes.c_float: "f32", ctypes.c_int: "i32", ctypes.c_int32: "i32"}[t]
+
+
+def test_ctypes_argtypes_match_the_header_prototypes_parameter_by_parameter():
+    """An argument added to the header but not to the binding (or bound with the wrong width) corrupts the call
+    silently; compare every prototype with the ctypes signature."""
+    lib = _lib.load()
+    protos = _prototypes()
+    assert sorted(protos) == sorted(_lib.SYMBOLS)
+    for name, params in protos.items():
+        argtypes = getattr(lib, name).argtypes
+        assert argtypes is not None, f"{name}: no argtypes set"
+        got = [_kind_of_ctypes(t) for t in argtypes]
+        want = [_kind_of_c(p) for p in params]
+        # size_t and u64 are the same register class on LP64; keep them distinct anyway, except where ctypes
+        # aliases them (c_size_t is c_ulong is c_uint64 on this platform)
+        norm = lambda ks: ["u64" if k == "size" else k for k in ks]  # noqa: E731
+        assert norm(got) == norm(want), f"{name}: binding {got} vs header {want}"

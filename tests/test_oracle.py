@@ -50,6 +50,38 @@ def test_numpy_restatement_matches_torch(kind, bi, L):
         assert np.abs(g - p.grad.numpy()).max() < 1e-10
 
 
+@pytest.mark.parametrize("kind,bi,L", [("gru", False, 2), ("gru", True, 2), ("lstm", True, 2), ("lstm", False, 1)])
+def test_numpy_restatement_matches_torch_on_packed_ragged_batches(kind, bi, L):
+    """PackedSequence semantics (the `lengths` argument the CUDA kernels take) against stock torch, fwd + bwd."""
+    from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+
+    torch.manual_seed(1)
+    I, H, B, T = 10, 12, 5, 9
+    lengths = torch.tensor([9, 2, 5, 1, 7])
+    cls = torch.nn.GRU if kind == "gru" else torch.nn.LSTM
+    ref = cls(I, H, num_layers=L, bidirectional=bi).double()
+    x = torch.randn(T, B, I, dtype=torch.float64, requires_grad=True)
+    out = ref(pack_padded_sequence(x, lengths, enforce_sorted=False))
+    y, _ = pad_packed_sequence(out[0], total_length=T)
+    states = out[1] if isinstance(out[1], tuple) else (out[1],)
+    orc = NumpyRNN(kind, [p.detach().numpy() for p in ref.parameters()], L, bi)
+    res = orc.forward(x.detach().numpy(), lengths=lengths.numpy())
+    assert np.abs(res[0] - y.detach().numpy()).max() < 1e-12
+    for b in range(B):
+        assert np.abs(res[0][int(lengths[b]):, b]).max(initial=0.0) == 0.0   # padded output rows are exactly 0
+    for a, b in zip(res[1:], states):
+        assert np.abs(a - b.detach().numpy()).max() < 1e-12
+    dy = torch.randn_like(y)   # including garbage at padded positions: it must not reach any gradient
+    dstates = [torch.randn_like(s) for s in states]
+    (y * dy).sum().add(sum((s * d).sum() for s, d in zip(states, dstates))).backward()
+    dx, dparams = orc.backward(dy.numpy(), dstates[0].numpy(), dstates[1].numpy() if len(dstates) > 1 else None)
+    assert np.abs(dx - x.grad.numpy()).max() < 1e-11
+    for b in range(B):
+        assert np.abs(dx[int(lengths[b]):, b]).max(initial=0.0) == 0.0
+    for p, g in zip(ref.parameters(), dparams):
+        assert np.abs(g - p.grad.numpy()).max() < 1e-10
+
+
 def _single(case, cls, regression):
     arrays, meta = load_golden(case)
     model = cls(meta["cfg"], regression=regression)

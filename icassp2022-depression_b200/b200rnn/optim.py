@@ -81,6 +81,8 @@ class FlatAdamW:
 
     @torch.no_grad()
     def step(self) -> None:
+        if not all(g.flat_p.is_cuda for g in self.groups):
+            raise _lib.B200RNNError("b200rnn.FlatAdamW: parameters are not on a CUDA device - no CPU path")
         lib = _lib.load()
         stream = torch.cuda.current_stream().cuda_stream
         scale = 1.0 / self.world

@@ -23,10 +23,19 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _require_cuda(*named) -> None:
+    """Raw pointers go straight to CUDA kernels: a host tensor must fail here, loudly (no CPU path)."""
+    for name, t in named:
+        if t is not None and not t.is_cuda:
+            raise _lib.B200RNNError(f"b200rnn: {name} is on {t.device}; the fused shell kernels run on CUDA only "
+                                    "and have no CPU path")
+
+
 @torch.no_grad()
 def attention_pool(seq_tm: torch.Tensor, h_n: torch.Tensor, attention_layer: torch.nn.Module) -> torch.Tensor:
     """``attention_net_with_w`` on the time-major LSTM output ``seq_tm`` [T,B,2H] and ``h_n`` [L*D,B,H] -> [B,H]."""
     lib = _lib.load()
+    _require_cuda(("seq", seq_tm), ("h_n", h_n), ("attention weight", attention_layer[0].weight))
     T, B, H2 = seq_tm.shape
     H = H2 // 2
     lin = attention_layer[0]
@@ -44,6 +53,7 @@ def mlp_dropout(x: torch.Tensor, linear: torch.nn.Linear, p: float, training: bo
                 stream_id: int) -> torch.Tensor:
     """``Dropout(p) -> linear -> ReLU -> Dropout(p)`` for a square ``linear`` (fc_out / fc_audio of fusion_net)."""
     lib = _lib.load()
+    _require_cuda(("x", x), ("linear.weight", linear.weight), ("rng header", rng_hdr))
     B, n = x.shape
     assert linear.weight.shape == (n, n)
     out = torch.empty_like(x)
@@ -63,6 +73,7 @@ class FusedFuseStep:
         self.model = model
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         w = model.fc_final[0].weight
+        _require_cuda(("model (fc_final.0.weight)", w))
         dev = w.device
         self.w = w
         self.bucket = bucket  # b200rnn.dp.GradBucket over the trainable parameter(s), or None (single process)
@@ -99,6 +110,7 @@ class FusedFuseStep:
         """Runs the step; returns (probs [B,2], loss scalar tensor)."""
         lib = _lib.load()
         m = self.model
+        _require_cuda(("labels", labels), ("batch.audio", batch.audio), ("batch.text", batch.text))
         tf, af = self.features(batch)
         B = tf.shape[0]
         probs = torch.empty(B, 2, dtype=torch.float32, device=tf.device)

@@ -116,3 +116,18 @@ def test_reference_classes_build_on_the_dropin_when_installed():
         assert float(model_t.lstm_net.bias_ih_l0.abs().max()) == 0.0
     finally:
         b200rnn.uninstall()
+
+
+def test_fused_shell_entry_points_reject_host_tensors():
+    """They hand raw pointers to CUDA kernels; a CPU tensor must raise before any launch."""
+    from b200rnn import fused_head
+
+    att = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.ReLU())
+    with pytest.raises(b200rnn.B200RNNError, match="no CPU path"):
+        fused_head.attention_pool(torch.randn(3, 2, 16), torch.randn(4, 2, 8), att)
+    with pytest.raises(b200rnn.B200RNNError, match="no CPU path"):
+        fused_head.mlp_dropout(torch.randn(2, 8), torch.nn.Linear(8, 8), 0.3, True, None, 0)
+    model = b200rnn.fusion_net(text_embed_size=16, text_hidden_dims=128, rnn_layers=1, dropout=0.1, num_classes=2,
+                               audio_hidden_dims=128, audio_embed_size=16)
+    with pytest.raises(b200rnn.B200RNNError, match="no CPU path"):
+        b200rnn.FusedFuseStep(model)

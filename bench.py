@@ -33,6 +33,30 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+
+def usable_cores() -> int:
+    """Host threads this process may really use: affinity mask, capped by the cgroup CPU quota if any."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+# The OpenMP pool must be sized BEFORE torch is imported: a plain `python bench.py` on the GPU box would otherwise
+# start os.cpu_count() = 128 intra-op threads inside a 16-core cgroup quota; after the first parallel host copy they
+# spin, the cgroup throttles the whole process and the launching thread with it (round-1 N=1 e2e: 1.21-1.36 ms/step
+# against 0.90 with OMP_NUM_THREADS=1, profiles/README.md). torchrun sets OMP_NUM_THREADS=1 itself, which is why
+# only the N=1 line showed it.
+os.environ.setdefault("OMP_NUM_THREADS", str(usable_cores()))
+
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
@@ -68,22 +92,6 @@ def _emit(line: dict) -> None:
 
 def _log(msg: str) -> None:
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
-
-
-def usable_cores() -> int:
-    """Host threads this process may really use: affinity mask, capped by the cgroup CPU quota if any."""
-    try:
-        n = len(os.sched_getaffinity(0))
-    except Exception:
-        n = os.cpu_count() or 1
-    try:
-        with open("/sys/fs/cgroup/cpu.max") as fh:
-            quota, period = fh.read().split()
-        if quota != "max":
-            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
-    except Exception:
-        pass
-    return n
 
 
 def _peaks():
@@ -322,6 +330,7 @@ def run_ours(args) -> None:
         raise SystemExit("bench.py: no CUDA device — this implementation has no CPU path (use --impl reference)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    torch.set_num_threads(1)   # the timed loops are launch loops: no intra-op pool spinning beside them (see top)
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     n_gpus = world
@@ -584,17 +593,41 @@ def run_ours(args) -> None:
                           f"(oracle/ref_models.py on stock torch.nn CPU kernels, {cores} threads); with the reference's "
                           f"list->tensor conversion (fuse_net_whole.py:343) it is {v2:.1f} seq/s ({ms2:.0f} ms/step)"}
         _emit(line)
-    # Teardown: tearing an NCCL communicator down while captured graphs still hold its kernels can dead-lock
-    # (observed: 2-rank run hung in destroy_process_group after printing). Drop the graphs, sync, leave hard.
+    _teardown(graphs, e2e_graphs, world)
+
+
+def _teardown(graphs, e2e_graphs, world: int) -> None:
+    """Normal interpreter exit (the driver's exit hook records which .so files this process loaded).
+
+    Round 1 left with os._exit(0) because a 2-rank run once hung in destroy_process_group while captured graphs still
+    held NCCL kernels. Order that avoids it: drop the graphs, synchronise, barrier, destroy the group. A watchdog thread
+    covers the residual risk without hiding the process from exit hooks: if the teardown has not finished after 30 s it
+    runs the registered atexit functions itself and only then leaves hard.
+    """
+    import atexit
+    import threading
+
+    done = threading.Event()
+
+    def watchdog():
+        if not done.wait(30.0):
+            _log("teardown watchdog: destroy_process_group did not return in 30 s; running exit hooks, leaving hard")
+            try:
+                atexit._run_exitfuncs()
+            finally:
+                os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
     graphs.clear()
     e2e_graphs.clear()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
+        dist.destroy_process_group()
+    done.set()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
 
 
 def _finetune_variant(dev, iters: int = 10, warmup: int = 3) -> dict:

@@ -17,8 +17,28 @@ import torch.distributed as dist
 from .modules import _B200RNNBase
 
 
+ALIGN_FLOATS = 64   # every view starts on a 256-byte boundary (TMA bulk copies / float4 epilogues need 16 B)
+
+
+def _aligned_offsets(params: Iterable[torch.Tensor], align: int = ALIGN_FLOATS):
+    """Start offsets (in floats) of per-parameter views inside one flat buffer, each rounded up to ``align``."""
+    offs, off = [], 0
+    for p in params:
+        off = (off + align - 1) // align * align
+        offs.append(off)
+        off += p.numel()
+    return offs, off
+
+
 class GradBucket:
-    """Flat gradient bucket over the trainable parameters of ``model``."""
+    """Flat gradient bucket over the trainable parameters of ``model``.
+
+    ``p.grad`` of every trainable parameter is a view of ``flat``; the RNN wgrad kernels write into those views
+    directly. The reference loops call ``optimizer.zero_grad()`` (audio_gru_whole.py:183), which since torch 2.0 sets
+    ``p.grad = None``: the bucket notices dropped views and re-attaches them - RNN weights when their backward asks for
+    its targets (`_sink`), dense parameters at :meth:`allreduce` (a fresh ``.grad`` is copied in once and re-bound) - so
+    ``zero_grad()`` with either ``set_to_none`` value, :meth:`zero` and :meth:`zero_grad` all give the same numbers.
+    """
 
     def __init__(self, model: torch.nn.Module, process_group: Optional[dist.ProcessGroup] = None,
                  direct_rnn_grads: bool = True):
@@ -26,17 +46,18 @@ class GradBucket:
         if not self.params:
             raise ValueError("GradBucket: the model has no trainable parameter")
         dev = self.params[0].device
-        self.numel = sum(p.numel() for p in self.params)
+        offs, total = _aligned_offsets(self.params)
+        self.numel = total
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self._views = {}
-        off = 0
-        for p in self.params:
+        self._bound: List[tuple] = []
+        for p, off in zip(self.params, offs):
             v = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
-            p.grad = v                      # autograd accumulates into this view in place
-            self._views[p.data_ptr()] = v      # keyed by storage address: saved tensors may be re-wrapped
+            p.grad = v                            # autograd accumulates into this view in place
+            self._views[p.data_ptr()] = (p, v)    # keyed by storage address: saved tensors may be re-wrapped
+            self._bound.append((p, v))
         if direct_rnn_grads:
             for m in model.modules():
                 if isinstance(m, _B200RNNBase):
@@ -44,17 +65,52 @@ class GradBucket:
 
     # called from the RNN autograd function: where should the weight gradients be accumulated?
     def _sink(self, weights: Iterable[torch.Tensor]):
-        return [self._views.get(w.data_ptr()) for w in weights]
+        out = []
+        for w in weights:
+            ent = self._views.get(w.data_ptr())
+            if ent is None:
+                out.append(None)
+                continue
+            p, v = ent
+            if p.grad is None:                    # zero_grad(set_to_none=True) dropped the view: start from zero
+                v.zero_()
+                p.grad = v
+            elif p.grad.data_ptr() != v.data_ptr():   # someone installed a foreign .grad: fold it in, re-bind
+                v.copy_(p.grad)
+                p.grad = v
+            out.append(v)
+        return out
+
+    def reattach(self) -> None:
+        """Bring every ``p.grad`` back into the bucket (no-op when nothing was dropped)."""
+        for p, v in self._bound:
+            g = p.grad
+            if g is None:
+                v.zero_()
+                p.grad = v
+            elif g.data_ptr() != v.data_ptr():
+                v.copy_(g)
+                p.grad = v
 
     @property
     def nbytes(self) -> int:
         return self.numel * 4
 
+    @property
+    def grad_scale(self) -> float:
+        """1/world: what the optimiser kernel multiplies the summed gradient with (mean-reduced loss)."""
+        return 1.0 / self.world
+
     def zero(self) -> None:
+        self.reattach()
         self.flat.zero_()
 
+    zero_grad = zero
+
     def allreduce(self, average: bool = True) -> None:
-        """The step's single collective. ``average`` gives mean-reduced-loss semantics across shards."""
+        """The step's single collective. ``average`` gives mean-reduced-loss semantics across shards; pass
+        ``average=False`` when the optimiser kernel applies :attr:`grad_scale` itself (``b200rnn_adamw``)."""
+        self.reattach()
         if self.world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             if average:

@@ -54,8 +54,16 @@ def _make_desc(cfg: RNNConfig, B: int, T: int, save: bool, accumulate: bool = Fa
                      1 if cfg.training else 0, float(cfg.dropout), flags)
 
 
-def _stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream_ptr(device=None) -> int:
+    """Raw handle of the current stream OF ``device`` (not of the process-wide current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _on(device):
+    """Make ``device`` current around a library call: the C side queries / configures the CURRENT device
+    (``cudaFuncSetAttribute``, occupancy, SM count), and stock nn.GRU / nn.LSTM work on whatever device their tensors
+    live on, so the drop-in has to as well (module on cuda:1 while cuda:0 is the process default)."""
+    return torch.cuda.device(device)
 
 
 class _RNNFunction(torch.autograd.Function):
@@ -63,12 +71,14 @@ class _RNNFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_tm: torch.Tensor, cfg: RNNConfig, rng_state: Optional[torch.Tensor], grad_sink,
-                lengths: Optional[torch.Tensor], *weights: torch.Tensor):
+                lengths: Optional[torch.Tensor], save: bool, *weights: torch.Tensor):
         lib = _lib.load()
         T, B, _ = x_tm.shape
         H, L, D = cfg.hidden_size, cfg.num_layers, cfg.num_dirs
         dev = x_tm.device
-        save = any(ctx.needs_input_grad)
+        # `save` is decided by the caller: grad mode is always off in here, and needs_input_grad is True for
+        # requires_grad weights even under torch.no_grad() (it would allocate the reserve and store gates for nothing)
+        save = bool(save) and any(ctx.needs_input_grad)
         desc = _make_desc(cfg, B, T, save)
         rbytes, sbytes = _lib.workspace_bytes(desc)
         reserve = torch.empty(rbytes if save else 0, dtype=torch.uint8, device=dev)
@@ -83,12 +93,13 @@ class _RNNFunction(torch.autograd.Function):
         c_n = torch.empty(L * D, B, H, dtype=torch.float32, device=dev) if cfg.mode == _lib.LSTM else None
         params = _lib.ptr_array([w.data_ptr() for w in weights])
         if B > 0 and T > 0:
-            rc = lib.b200rnn_forward_fused(
-                ctypes.byref(desc), x_tm.data_ptr(), x_tm.stride(0), x_tm.stride(1), params,
-                y.data_ptr(), ys_t, ys_b, h_n.data_ptr(), c_n.data_ptr() if c_n is not None else None,
-                reserve.data_ptr() if save else None, scratch.data_ptr(),
-                0, 0, rng_state.data_ptr() if rng_state is not None else None, None, None, 0.0, None,
-                lengths.data_ptr() if lengths is not None else None, _stream_ptr())
+            with _on(dev):
+                rc = lib.b200rnn_forward_fused(
+                    ctypes.byref(desc), x_tm.data_ptr(), x_tm.stride(0), x_tm.stride(1), params,
+                    y.data_ptr(), ys_t, ys_b, h_n.data_ptr(), c_n.data_ptr() if c_n is not None else None,
+                    reserve.data_ptr() if save else None, scratch.data_ptr(),
+                    0, 0, rng_state.data_ptr() if rng_state is not None else None, None, None, 0.0, None,
+                    lengths.data_ptr() if lengths is not None else None, _stream_ptr(dev))
             _lib.check(rc, "b200rnn_forward")
         else:
             h_n.zero_()
@@ -135,7 +146,7 @@ class _RNNFunction(torch.autograd.Function):
         # weight gradients: either straight into caller-provided views (a flat all-reduce bucket) or into one
         # fresh flat buffer that is returned to autograd as views
         sink = ctx.grad_sink
-        w_needed = [ctx.needs_input_grad[5 + i] for i in range(len(weights))]
+        w_needed = [ctx.needs_input_grad[6 + i] for i in range(len(weights))]
         grads_out: list = [None] * len(weights)
         accumulate = False
         if sink is not None:
@@ -161,21 +172,22 @@ class _RNNFunction(torch.autograd.Function):
         params = _lib.ptr_array([w.data_ptr() for w in weights])
         dparams = _lib.ptr_array(dptrs)
         if B > 0 and T > 0:
-            rc = lib.b200rnn_backward(
-                ctypes.byref(desc), x_tm.data_ptr(), x_tm.stride(0), x_tm.stride(1), params,
-                y.data_ptr(), ys_t, ys_b, dy.data_ptr(), dys_t, dys_b,
-                dh_n.data_ptr() if dh_n is not None else None,
-                dc_n.data_ptr() if dc_n is not None else None,
-                reserve.data_ptr(), scratch.data_ptr(),
-                dx.data_ptr() if dx is not None else None,
-                dx.stride(0) if dx is not None else 0, dx.stride(1) if dx is not None else 0,
-                dparams, ctx.lengths.data_ptr() if ctx.lengths is not None else None, _stream_ptr())
+            with _on(dev):
+                rc = lib.b200rnn_backward(
+                    ctypes.byref(desc), x_tm.data_ptr(), x_tm.stride(0), x_tm.stride(1), params,
+                    y.data_ptr(), ys_t, ys_b, dy.data_ptr(), dys_t, dys_b,
+                    dh_n.data_ptr() if dh_n is not None else None,
+                    dc_n.data_ptr() if dc_n is not None else None,
+                    reserve.data_ptr(), scratch.data_ptr(),
+                    dx.data_ptr() if dx is not None else None,
+                    dx.stride(0) if dx is not None else 0, dx.stride(1) if dx is not None else 0,
+                    dparams, ctx.lengths.data_ptr() if ctx.lengths is not None else None, _stream_ptr(dev))
             _lib.check(rc, "b200rnn_backward")
         else:
             for g in grads_out:
                 if g is not None:
                     g.zero_()
-        return (dx, None, None, None, None, *grads_out)
+        return (dx, None, None, None, None, None, *grads_out)
 
 
 def rnn_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNNConfig,
@@ -197,7 +209,11 @@ def rnn_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNNConfig
     x_tm = _tm_view(x_tm)
     if lengths is not None:
         lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
-    return _RNNFunction.apply(x_tm, cfg, rng_state, grad_sink, lengths, *weights)
+    for i, w in enumerate(weights):
+        if w.device != x.device:
+            raise _lib.B200RNNError(f"b200rnn: weight[{i}] is on {w.device} but the input is on {x.device}")
+    save = torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in weights))
+    return _RNNFunction.apply(x_tm, cfg, rng_state, grad_sink, lengths, save, *weights)
 
 
 @torch.no_grad()
@@ -230,12 +246,14 @@ def rnn_forward_fused(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNN
     h_n = torch.empty(L * D, B, H, dtype=torch.float32, device=dev)
     c_n = torch.empty(L * D, B, H, dtype=torch.float32, device=dev) if cfg.mode == _lib.LSTM else None
     params = _lib.ptr_array([w.data_ptr() for w in weights])
-    rc = lib.b200rnn_forward_fused(
-        ctypes.byref(desc), x_tm.data_ptr(), x_tm.stride(0), x_tm.stride(1), params, y_ptr, ys_t, ys_b,
-        h_n.data_ptr(), c_n.data_ptr() if c_n is not None else None, None, scratch.data_ptr(), 0, 0,
-        rng_state.data_ptr() if rng_state is not None else None,
-        ln_weight.data_ptr() if ln_weight is not None else None, ln_bias.data_ptr() if ln_bias is not None else None,
-        float(ln_eps), pool_ptr, None, _stream_ptr())
+    with _on(dev):
+        rc = lib.b200rnn_forward_fused(
+            ctypes.byref(desc), x_tm.data_ptr(), x_tm.stride(0), x_tm.stride(1), params, y_ptr, ys_t, ys_b,
+            h_n.data_ptr(), c_n.data_ptr() if c_n is not None else None, None, scratch.data_ptr(), 0, 0,
+            rng_state.data_ptr() if rng_state is not None else None,
+            ln_weight.data_ptr() if ln_weight is not None else None,
+            ln_bias.data_ptr() if ln_bias is not None else None,
+            float(ln_eps), pool_ptr, None, _stream_ptr(dev))
     _lib.check(rc, "b200rnn_forward_fused")
     return (out, h_n) if c_n is None else (out, h_n, c_n)
 
@@ -262,9 +280,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kcontig: bool = True, b_kcontig:
         assert not accumulate
     sbytes = max(M * N * 4 * 64, 8 * (M + N) * K + 4096) if use_splitk else 0
     scratch = torch.empty(sbytes, dtype=torch.uint8, device=a.device) if sbytes else None
-    rc = lib.b200rnn_gemm_f32(M, N, K, a.data_ptr(), lda, int(a_kcontig), b.data_ptr(), ldb,
-                              int(b_kcontig), out.data_ptr(), out.stride(0),
-                              bias.data_ptr() if bias is not None else None, int(accumulate),
-                              scratch.data_ptr() if scratch is not None else None, sbytes, _stream_ptr())
+    with _on(a.device):
+        rc = lib.b200rnn_gemm_f32(M, N, K, a.data_ptr(), lda, int(a_kcontig), b.data_ptr(), ldb,
+                                  int(b_kcontig), out.data_ptr(), out.stride(0),
+                                  bias.data_ptr() if bias is not None else None, int(accumulate),
+                                  scratch.data_ptr() if scratch is not None else None, sbytes, _stream_ptr(a.device))
     _lib.check(rc, "b200rnn_gemm_f32")
     return out

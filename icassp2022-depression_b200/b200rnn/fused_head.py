@@ -15,12 +15,12 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .functional import rnn_forward_fused
+from .functional import _on, rnn_forward_fused
 from .staging import FuseBatch
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def _require_cuda(*named) -> None:
@@ -42,9 +42,11 @@ def attention_pool(seq_tm: torch.Tensor, h_n: torch.Tensor, attention_layer: tor
     ctx = torch.empty(B, H, dtype=torch.float32, device=seq_tm.device)
     h_n = h_n.contiguous()
     assert seq_tm.stride(2) == 1
-    _lib.check(lib.b200rnn_attention_pool(seq_tm.data_ptr(), seq_tm.stride(0), seq_tm.stride(1), h_n.data_ptr(),
-                                          h_n.shape[0], B, T, H, lin.weight.data_ptr(), lin.bias.data_ptr(),
-                                          ctx.data_ptr(), _stream()), "b200rnn_attention_pool")
+    with _on(seq_tm.device):
+        rc = lib.b200rnn_attention_pool(seq_tm.data_ptr(), seq_tm.stride(0), seq_tm.stride(1), h_n.data_ptr(),
+                                        h_n.shape[0], B, T, H, lin.weight.data_ptr(), lin.bias.data_ptr(),
+                                        ctx.data_ptr(), _stream(seq_tm.device))
+    _lib.check(rc, "b200rnn_attention_pool")
     return ctx
 
 
@@ -57,10 +59,11 @@ def mlp_dropout(x: torch.Tensor, linear: torch.nn.Linear, p: float, training: bo
     B, n = x.shape
     assert linear.weight.shape == (n, n)
     out = torch.empty_like(x)
-    _lib.check(lib.b200rnn_mlp_dropout(x.data_ptr(), B, n, linear.weight.data_ptr(), linear.bias.data_ptr(),
-                                       out.data_ptr(), int(training), float(p),
-                                       rng_hdr.data_ptr() if rng_hdr is not None else None, stream_id, _stream()),
-               "b200rnn_mlp_dropout")
+    with _on(x.device):
+        rc = lib.b200rnn_mlp_dropout(x.data_ptr(), B, n, linear.weight.data_ptr(), linear.bias.data_ptr(),
+                                     out.data_ptr(), int(training), float(p),
+                                     rng_hdr.data_ptr() if rng_hdr is not None else None, stream_id, _stream(x.device))
+    _lib.check(rc, "b200rnn_mlp_dropout")
     return out
 
 
@@ -113,6 +116,12 @@ class FusedFuseStep:
         _require_cuda(("labels", labels), ("batch.audio", batch.audio), ("batch.text", batch.text))
         tf, af = self.features(batch)
         B = tf.shape[0]
+        # the kernel reads `const int64_t labels[B]`: anything else (int32 from numpy, float, a strided view) would be
+        # silently misread, so it is converted here; the values must be class indices 0/1 (checked on the device)
+        if labels.dtype != torch.int64 or not labels.is_contiguous():
+            labels = labels.to(torch.int64).contiguous()
+        if labels.numel() != B:
+            raise ValueError(f"FusedFuseStep: {labels.numel()} labels for a batch of {B}")
         probs = torch.empty(B, 2, dtype=torch.float32, device=tf.device)
         _lib.check(lib.b200rnn_fuse_loss_grad(tf.data_ptr(), tf.shape[1], af.data_ptr(), af.shape[1], labels.data_ptr(), B,
                                               self.w.data_ptr(), self.grad.data_ptr(), 0, self.loss.data_ptr(),

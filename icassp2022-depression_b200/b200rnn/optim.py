@@ -14,6 +14,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from .dp import _aligned_offsets
 from .modules import _B200RNNBase
 
 
@@ -22,19 +23,20 @@ class _Group:
         self.params = params
         self.weight_decay = float(weight_decay)
         dev = params[0].device
-        n = sum(p.numel() for p in params)
-        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        offs, n = _aligned_offsets(params)     # 256-byte aligned views: weight_hh feeds TMA bulk copies
+        self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
+        self.views = []
         with torch.no_grad():
-            for p in params:
+            for p, off in zip(params, offs):
                 k = p.numel()
                 self.flat_p[off:off + k].copy_(p.reshape(-1))
                 p.data = self.flat_p[off:off + k].view_as(p)       # parameter now lives in the flat buffer
-                p.grad = self.flat_g[off:off + k].view_as(p)       # autograd accumulates into the flat gradient
-                off += k
+                g = self.flat_g[off:off + k].view_as(p)
+                p.grad = g                                         # autograd accumulates into the flat gradient
+                self.views.append((p, g))
 
 
 class FlatAdamW:
@@ -53,10 +55,25 @@ class FlatAdamW:
         self.process_group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         if model is not None:   # RNN wgrad kernels write straight into the flat gradient views
-            views = {p.data_ptr(): p.grad for g in self.groups for p in g.params}
+            views = {p.data_ptr(): (p, v) for g in self.groups for p, v in g.views}
+
+            def sink(weights, _v=views):
+                out = []
+                for w in weights:
+                    ent = _v.get(w.data_ptr())
+                    if ent is None:
+                        out.append(None)
+                        continue
+                    p, v = ent
+                    if p.grad is None:            # a foreign zero_grad(set_to_none=True): restart this view from zero
+                        v.zero_()
+                        p.grad = v
+                    out.append(v)
+                return out
+
             for mod in model.modules():
                 if isinstance(mod, _B200RNNBase):
-                    mod._grad_sink = lambda weights, _v=views: [_v.get(w.data_ptr()) for w in weights]
+                    mod._grad_sink = sink
 
     @classmethod
     def like_reference(cls, model: torch.nn.Module, lr: float, weight_decay: float = 1e-5, **kw) -> "FlatAdamW":
@@ -69,12 +86,25 @@ class FlatAdamW:
             groups.append({"params": no_decay, "weight_decay": 0.0})
         return cls(groups, lr, model=model, **kw)
 
-    def zero_grad(self) -> None:
+    def reattach(self) -> None:
+        """Re-bind ``p.grad`` views dropped by someone else's ``zero_grad(set_to_none=True)``; fold in fresh grads."""
+        for g in self.groups:
+            for p, v in g.views:
+                if p.grad is None:
+                    v.zero_()
+                    p.grad = v
+                elif p.grad.data_ptr() != v.data_ptr():
+                    v.copy_(p.grad)
+                    p.grad = v
+
+    def zero_grad(self, set_to_none: bool = False) -> None:   # the views are the optimiser's own storage: never dropped
+        self.reattach()
         for g in self.groups:
             g.flat_g.zero_()
 
     def allreduce(self) -> None:
         """One collective per group (the reference's two groups could be merged; kept separate for clarity)."""
+        self.reattach()
         if self.world > 1:
             for g in self.groups:
                 dist.all_reduce(g.flat_g, op=dist.ReduceOp.SUM, group=self.process_group)
@@ -84,11 +114,14 @@ class FlatAdamW:
         if not all(g.flat_p.is_cuda for g in self.groups):
             raise _lib.B200RNNError("b200rnn.FlatAdamW: parameters are not on a CUDA device - no CPU path")
         lib = _lib.load()
-        stream = torch.cuda.current_stream().cuda_stream
+        self.reattach()
+        dev = self.groups[0].flat_p.device
         scale = 1.0 / self.world
-        for i, g in enumerate(self.groups):
-            last = i == len(self.groups) - 1
-            _lib.check(lib.b200rnn_adamw(g.flat_p.data_ptr(), g.flat_g.data_ptr(), g.m.data_ptr(), g.v.data_ptr(),
-                                         self.step_count.data_ptr(), g.flat_p.numel(), self.lr, self.betas[0],
-                                         self.betas[1], self.eps, g.weight_decay, scale, int(last), stream),
-                       "b200rnn_adamw")
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            for i, g in enumerate(self.groups):
+                last = i == len(self.groups) - 1
+                _lib.check(lib.b200rnn_adamw(g.flat_p.data_ptr(), g.flat_g.data_ptr(), g.m.data_ptr(), g.v.data_ptr(),
+                                             self.step_count.data_ptr(), g.flat_p.numel(), self.lr, self.betas[0],
+                                             self.betas[1], self.eps, g.weight_decay, scale, int(last), stream),
+                           "b200rnn_adamw")

@@ -482,18 +482,21 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
         float* dGT = S + sl.b_tc_dgT;  // [GH][ldk]
         float* hnT = S + sl.b_tc_hnT;  // [H][ldk]   (GRU: dn * r)
         const TcOperand opX{xT, xT + (size_t)Il * ldk, ldk};
-        if (dw_ih || dw_hh) {
+        // the tcgen05 epilogue stores float4: a gradient target that is not 16-byte aligned (a view into a caller's
+        // flat bucket behind an odd-sized tensor) takes the FFMA GEMM below instead of failing
+        const bool tc_wih = dw_ih && aligned_to(dw_ih, 16), tc_whh = dw_hh && aligned_to(dw_hh, 16);
+        if (tc_wih || tc_whh) {
           rc = tc_split_transpose(dG, simple_rows((long long)d.GH), (int)d.TB, (int)d.GH, dGT, dGT + d.GH * ldk, ldk, st);
           if (rc) return rc;
         }
-        if (dw_ih) {  // dW_ih[GH, Il] = dGi^T[GH, TB] * X_l^T[Il, TB]^T
+        if (tc_wih) {  // dW_ih[GH, Il] = dGi^T[GH, TB] * X_l^T[Il, TB]^T
           const TcOperand opA{dGT, dGT + d.GH * ldk, ldk};
           rc = tc_gemm_presplit(opA, opX, (int)d.GH, Il, (int)d.TB, dw_ih, simple_rows(Il), nullptr, nullptr, 0,
                                 accumulate, S + sl.b_tc_part, sl.b_tc_part_bytes, st);
           if (rc) return rc;
           done_dwih = true;
         }
-        if (dw_hh && d.T > 1 && d.B % 4 == 0) {
+        if (tc_whh && d.T > 1 && d.B % 4 == 0) {
           // dW_hh = sum_t dGh[t]^T h_{prev(t)}: columns of the transposed operands are (t,b) flattened time-major,
           // so the one-step shift is a column offset of B (forward: dG[t] with y[t-1]; reverse: dG[t] with y[t+1])
           float* yT = S + sl.b_tc_yT;  // [H][ldk]

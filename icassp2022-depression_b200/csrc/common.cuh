@@ -21,6 +21,20 @@ void count_launch(int n = 1);  // bumps the counter behind b200rnn_launch_count(
     }                                                                                              \
   } while (0)
 
+// ---- per-device state ----------------------------------------------------------------------------
+// cudaFuncSetAttribute and the occupancy queries are per device: every "done once" cache of the launchers is keyed by
+// the CURRENT device ordinal, so a process that drives several GPUs (or a module living on cuda:1 while cuda:0 is the
+// process default) sets the attributes on each of them. The Python bridge makes the tensor's device current first.
+constexpr int MAX_DEVICES = 64;
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) {
+    cudaGetLastError();
+    d = 0;
+  }
+  return (d < 0 || d >= MAX_DEVICES) ? 0 : d;
+}
+
 // ---- two-level row addressing ------------------------------------------------------------------
 // A logical row index r = outer*inner_n + inner maps to element offset
 //   outer*s_outer + inner*s_inner.

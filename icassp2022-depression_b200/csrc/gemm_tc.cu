@@ -527,12 +527,13 @@ int tc_gemm_presplit(const TcOperand& A, const TcOperand& B, int M, int N, int K
     return B200RNN_ERR_CUDA;
   }
   static std::mutex mu;
-  static bool attr_done = false;
+  static bool attr_done[MAX_DEVICES] = {false};
   {
+    const int dev = current_device();
     std::lock_guard<std::mutex> lk(mu);
-    if (!attr_done) {
+    if (!attr_done[dev]) {
       B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-      attr_done = true;
+      attr_done[dev] = true;
     }
   }
   int sms = 148;

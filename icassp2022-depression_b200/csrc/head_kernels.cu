@@ -295,10 +295,10 @@ B200RNN_API int b200rnn_mlp_dropout(const float* x, int B, int n, const float* W
     set_error("mlp_dropout: width %d too large", n);
     return B200RNN_ERR_UNSUPPORTED;
   }
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[MAX_DEVICES] = {false};
+  if (!attr[current_device()]) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(mlp_dropout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
+    attr[current_device()] = true;
   }
   dim3 grid((n + MLP_TI - 1) / MLP_TI, (B + MLP_TB - 1) / MLP_TB);
   mlp_dropout_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream_)>>>(x, B, n, W, bias, out, training, p, rng_hdr,
@@ -321,10 +321,10 @@ B200RNN_API int b200rnn_fuse_loss_grad(const float* text_feature, int Ht, const 
     set_error("fuse_loss_grad: feature width %d too large", F);
     return B200RNN_ERR_UNSUPPORTED;
   }
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[MAX_DEVICES] = {false};
+  if (!attr[current_device()]) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(fuse_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
+    attr[current_device()] = true;
   }
   fuse_loss_grad_kernel<<<1, LOSS_THREADS, smem, static_cast<cudaStream_t>(stream_)>>>(
       text_feature, Ht, audio_feature, Ha, reinterpret_cast<const long long*>(labels), B, W, dW, accumulate, loss, probs);

@@ -163,77 +163,6 @@ __device__ __forceinline__ void dots_chunk2(const float* __restrict__ W_s, int g
   }
 }
 
-// EXPERIMENTAL (rec_fwd_tm_kernel): the chunk contraction of a 3-gate layer with the three weight blocks in three
-// different on-chip stores - gate 0 in shared memory, gate 1 in TENSOR MEMORY (thread-private: 16 columns of this
-// thread's TMEM lane per chunk, fetched with tcgen05.ld 32x32b.x16 while gate 0 is being multiplied), gate 2 in
-// registers. TMEM is otherwise idle in this kernel and adds 64 B/cycle/SM of operand bandwidth next to the 128 B/cycle
-// of shared memory. taddr_c = TMEM address (lane quarter of the warp, first column of loop chunk c).
-template <int KL, int UPL, int BS, int KLEN, int VSTRIDE>
-__device__ __forceinline__ void dots_chunk2_tm(const float* __restrict__ W_s, int row0,
-                                               const float (&wreg)[1][UPL][KLEN / KL], uint32_t taddr_c,
-                                               const float* __restrict__ vec_s, int c, int ca, int lane,
-                                               float2 (&acc)[3][UPL][BS]) {
-  using LM = LaneMap<KL, UPL, BS>;
-  static_assert(UPL == 4, "one x16 tensor-memory load per chunk = 4 units x 4 k");
-  const int kl = LM::kl(lane), p = LM::p(lane), q = LM::q(lane), cgrp = LM::cl(lane);
-  const int koff = ca * 4 * KL + kl * 4;
-  uint32_t t[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]),
-        "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
-      : "r"(taddr_c)
-      : "memory");
-  float4 hv[BS];
-#pragma unroll
-  for (int ab = 0; ab < BS; ++ab) hv[ab] = *reinterpret_cast<const float4*>(&vec_s[(ab ^ q) * VSTRIDE + koff]);
-  // gate 0: shared memory
-#pragma unroll
-  for (int au = 0; au < UPL; ++au) {
-    const int row = row0 + cgrp * UPL + (au ^ p);
-    const float4 wv = *reinterpret_cast<const float4*>(&W_s[row * KLEN + koff]);
-#pragma unroll
-    for (int ab = 0; ab < BS; ++ab) {
-      float2 a = acc[0][au][ab];
-      a = __ffma2_rn(make_float2(wv.x, wv.y), make_float2(hv[ab].x, hv[ab].y), a);
-      a = __ffma2_rn(make_float2(wv.z, wv.w), make_float2(hv[ab].z, hv[ab].w), a);
-      acc[0][au][ab] = a;
-    }
-  }
-  // gate 1: tensor memory. The registers are in/out operands of the wait so that no use can be scheduled above it.
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]),
-                 "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
-               :
-               : "memory");
-#pragma unroll
-  for (int au = 0; au < UPL; ++au) {
-    const float4 wv = make_float4(__uint_as_float(t[au * 4 + 0]), __uint_as_float(t[au * 4 + 1]),
-                                  __uint_as_float(t[au * 4 + 2]), __uint_as_float(t[au * 4 + 3]));
-#pragma unroll
-    for (int ab = 0; ab < BS; ++ab) {
-      float2 a = acc[1][au][ab];
-      a = __ffma2_rn(make_float2(wv.x, wv.y), make_float2(hv[ab].x, hv[ab].y), a);
-      a = __ffma2_rn(make_float2(wv.z, wv.w), make_float2(hv[ab].z, hv[ab].w), a);
-      acc[1][au][ab] = a;
-    }
-  }
-  // gate 2: registers
-#pragma unroll
-  for (int au = 0; au < UPL; ++au) {
-    const float4 wv = make_float4(wreg[0][au][c * 4 + 0], wreg[0][au][c * 4 + 1], wreg[0][au][c * 4 + 2],
-                                  wreg[0][au][c * 4 + 3]);
-#pragma unroll
-    for (int ab = 0; ab < BS; ++ab) {
-      float2 a = acc[2][au][ab];
-      a = __ffma2_rn(make_float2(wv.x, wv.y), make_float2(hv[ab].x, hv[ab].y), a);
-      a = __ffma2_rn(make_float2(wv.z, wv.w), make_float2(hv[ab].z, hv[ab].w), a);
-      acc[2][au][ab] = a;
-    }
-  }
-}
-
 template <int NR, int UPL, int BS>
 __device__ __forceinline__ void fold_pairs(const float2 (&acc2)[NR][UPL][BS], float (&acc)[NR][UPL][BS]) {
 #pragma unroll

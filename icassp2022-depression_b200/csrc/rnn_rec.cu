@@ -284,199 +284,6 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
 }
 
 // =================================================================================================
-// forward, EXPERIMENTAL variant (B200RNN_FWD_VARIANT=6, GRU only, not validated on hardware yet): rec_fwd_kernel
-// with the z gate block moved from shared memory into tensor memory (rnn_core.cuh: dots_chunk2_tm). Per step it takes
-// a third of the weight reads off the shared-memory pipe (1 280 -> 768 wavefront cycles per step and SM) and puts them
-// on the TMEM read path (64 KB per step at 64 B/cycle), which the FFMA kernel otherwise leaves idle. Everything else
-// (clusters, exchange, gate math, stores) is rec_fwd_kernel<GRU, H, C, BS, KL, UPL, RG = 1>, fixed-length only.
-// =================================================================================================
-template <int H, int C, int BS, int KL, int UPL>
-struct TmCfg {
-  using Base = RecCfg<B200RNN_GRU, H, C, BS, KL, UPL, 1>;
-  static constexpr int HS = Base::HS, NT = Base::NT, NW = Base::NW, NCH = Base::NCH;
-  static constexpr int TCOLS = (NW / 4) * NCH * UPL * 4;  // tensor-memory columns: two warps share a lane quarter
-  static constexpr size_t SMEM = (size_t)HS * H * sizeof(float) /* r gate */ + (size_t)2 * BS * H * sizeof(float) +
-                                 Base::BAR_BYTES + 16 /* TMEM address slot */;
-  static_assert(NW % 4 == 0, "whole warpgroups: every TMEM lane quarter is covered");
-  static_assert(TCOLS == 32 || TCOLS == 64 || TCOLS == 128 || TCOLS == 256 || TCOLS == 512, "TMEM allocation size");
-};
-
-template <int H, int C, int BS, int KL, int UPL>
-__global__ void __launch_bounds__(TmCfg<H, C, BS, KL, UPL>::NT, 1)
-    rec_fwd_tm_kernel(const RecFwdParams p, const int nslices) {
-  using Cfg = RecCfg<B200RNN_GRU, H, C, BS, KL, UPL, 1>;
-  using Tm = TmCfg<H, C, BS, KL, UPL>;
-  using LM = LaneMap<KL, UPL, BS>;
-  constexpr int G = 3, HS = Cfg::HS, NT = Cfg::NT, UPW = Cfg::UPW, GH = G * H;
-  constexpr int NCH = Cfg::NCH, CPS = Cfg::CPS;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* W_s = reinterpret_cast<float*>(smem_raw);                 // [HS][H]: rows of the r gate block
-  float* h_s = W_s + (size_t)HS * H;                               // [2][BS][H]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(h_s + 2 * BS * H);  // [0] weights, [1 + buf*C + src] state slices
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(bars) + Cfg::BAR_BYTES);
-
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const uint32_t rank = ptx::cluster_ctarank();
-  const int cid = blockIdx.x / C;
-  const int dir = cid / nslices;
-  const int slice = cid - dir * nslices;
-  const int b0 = slice * BS;
-  const int j0 = (int)rank * HS;
-  const int B = p.B, T = p.T;
-  const float* w_hh = p.w_hh[dir];
-
-  if (tid == 0) {
-    for (int i = 0; i < Cfg::NBAR; ++i) ptx::mbar_init(&bars[i], 1);
-    ptx::fence_mbar_init();
-  }
-  if (w == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(tmem_slot)),
-                 "r"((uint32_t)Tm::TCOLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  // this thread's window of tensor memory: lane quarter of its warp, column block of its warpgroup
-  const uint32_t tm_thread = *tmem_slot + ((uint32_t)((w & 3) * 32) << 16) + (uint32_t)((w >> 2) * NCH * UPL * 4);
-  if (tid == 0) {
-    ptx::mbar_arrive_expect_tx(&bars[0], (uint32_t)(HS * H * sizeof(float)));
-    ptx::tma_bulk_g2s(W_s, w_hh + (size_t)j0 * H, (uint32_t)(HS * H * sizeof(float)), &bars[0]);  // r gate rows
-  }
-  for (int i = tid; i < 2 * BS * H; i += NT) h_s[i] = 0.f;  // h_0 = 0 (rnn.py:1432-1440)
-  const int rot = Cfg::ROT ? (int)rank * CPS : 0;
-  {
-    // z gate block -> tensor memory, in the rotated chunk order of the loop: column c*16 + au*4 + e of this thread's
-    // lane holds W_hz[unit(au)][ca*4*KL + kl*4 + e] (what load_resident would put into wreg[.][au][c*4 + e])
-    const int kl = LM::kl(lane), pp = LM::p(lane), cgrp = LM::cl(lane);
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int ca = (c + rot) % NCH;
-      uint32_t r[16];
-#pragma unroll
-      for (int au = 0; au < UPL; ++au) {
-        const float* row = w_hh + ((size_t)1 * H + j0 + w * UPW + cgrp * UPL + (au ^ pp)) * H;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(row + ca * 4 * KL + kl * 4));
-        r[au * 4 + 0] = __float_as_uint(v.x);
-        r[au * 4 + 1] = __float_as_uint(v.y);
-        r[au * 4 + 2] = __float_as_uint(v.z);
-        r[au * 4 + 3] = __float_as_uint(v.w);
-      }
-      asm volatile(
-          "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
-          "%15, %16};" ::"r"(tm_thread + (uint32_t)(c * UPL * 4)),
-          "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-          : "memory");
-    }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-  }
-  float wreg[1][UPL][H / KL];
-  load_resident<1, KL, UPL, BS, H>(w_hh, H, (long long)2 * H + j0 + w * UPW, rot, lane, wreg);  // n gate block
-  ptx::mbar_wait(&bars[0], 0);
-  __syncthreads();
-  ptx::cluster_sync_all();  // peers' barriers and state buffers are initialised before anyone writes into them
-
-  const int uw = LM::unit(lane), qb = LM::q(lane);
-  const int j = j0 + w * UPW + uw;  // hidden unit
-  const int b = b0 + qb;            // batch row
-  const bool valid = b < B;
-  float* gates = p.gates[dir];
-  float* extra = p.extra[dir];
-  const float bhn = p.b_hh[dir][2 * H + j];
-
-  float h_prev = 0.f, h_sum = 0.f;
-  float gi[G];
-#pragma unroll
-  for (int g = 0; g < G; ++g) gi[g] = 0.f;
-  if (valid && T > 0) {
-    const int t0 = dir ? T - 1 : 0;
-    const float* gp = gates + ((size_t)t0 * B + b) * GH + j;
-#pragma unroll
-    for (int g = 0; g < G; ++g) gi[g] = gp[g * H];
-  }
-
-  for (int step = 0; step < T; ++step) {
-    const int t = dir ? (T - 1 - step) : step;
-    const int cur = step & 1, nxt = cur ^ 1;
-    const float* h_cur = h_s + cur * BS * H;
-    float* h_nxt = h_s + nxt * BS * H;
-    const uint32_t par = ((step - 1) >> 1) & 1;
-
-    float2 acc2[G][UPL][BS];
-    float acc[G][UPL][BS];
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-#pragma unroll
-      for (int au = 0; au < UPL; ++au)
-#pragma unroll
-        for (int ab = 0; ab < BS; ++ab) acc2[g][au][ab] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int ca = (c + rot) % NCH;
-      if (step > 0) {
-        if (Cfg::ROT) {
-          if (c % CPS == 0) ptx::mbar_wait(&bars[1 + cur * C + ca / CPS], par);
-        } else {
-#pragma unroll
-          for (int s2 = 0; s2 < Cfg::SPC; ++s2) ptx::mbar_wait(&bars[1 + cur * C + ca * Cfg::SPC + s2], par);
-        }
-      }
-      dots_chunk2_tm<KL, UPL, BS, H, H>(W_s, w * UPW, wreg, tm_thread + (uint32_t)(c * UPL * 4), h_cur, c, ca, lane,
-                                        acc2);
-    }
-    if (tid == 0 && step + 1 < T) {
-#pragma unroll
-      for (int src = 0; src < C; ++src)
-        ptx::mbar_arrive_expect_tx(&bars[1 + nxt * C + src], (uint32_t)(BS * HS * sizeof(float)));
-    }
-    fold_pairs<G, UPL, BS>(acc2, acc);
-    warp_transpose_reduce<G, KL, UPL, BS>(acc);
-
-    const float r = sigmoid_f(gi[0] + acc[0][0][0]);
-    const float z = sigmoid_f(gi[1] + acc[1][0][0]);
-    const float hn = acc[2][0][0] + bhn;
-    const float n = tanh_f(gi[2] + r * hn);
-    const float hnew = n + z * (h_prev - n);
-    h_prev = hnew;
-    h_sum += hnew;
-
-    if (step + 1 < T)
-      allgather_units<C, KL, UPL, BS>(hnew, h_nxt, H, j0 + w * UPW, &bars[1 + nxt * C + rank], lane);
-
-    if (valid) {
-      if (p.y) p.y[(long long)t * p.y_st + (long long)b * p.y_sb + dir * H + j] = hnew;
-      if (p.training) {
-        float* gp = gates + ((size_t)t * B + b) * GH + j;
-        gp[0] = r;
-        gp[H] = z;
-        gp[2 * H] = n;
-        extra[((size_t)t * B + b) * H + j] = hn;
-      }
-      if (step == T - 1) {
-        p.h_n[((size_t)dir * B + b) * H + j] = hnew;
-        if (p.y_pool) p.y_pool[(size_t)b * p.D * H + dir * H + j] = h_sum;
-      }
-      if (step + 1 < T) {
-        const int tn = dir ? (T - 2 - step) : (step + 1);
-        const float* gp = gates + ((size_t)tn * B + b) * GH + j;
-#pragma unroll
-        for (int g = 0; g < G; ++g) gi[g] = gp[g * H];
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (w == 0) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"((uint32_t)Tm::TCOLS)
-                 : "memory");
-  }
-  ptx::cluster_sync_all();  // nobody exits while a peer could still address its shared memory
-}
-
-// =================================================================================================
 // backward (BPTT)
 // =================================================================================================
 // w_prep layout (written by whh_prep_kernel): [C ranks][G][HS][H],
@@ -714,14 +521,19 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
 // =================================================================================================
 template <typename K>
 int prepare_kernel(K kernel, size_t smem) {
+  struct Done {
+    const void* k;
+    int dev;
+  };
   static std::mutex mu;  // forward and autograd-backward threads both launch
-  static const void* done[128];
+  static Done done[256];
   static int ndone = 0;
+  const int dev = current_device();
   std::lock_guard<std::mutex> lk(mu);
   for (int i = 0; i < ndone; ++i)
-    if (done[i] == (const void*)kernel) return B200RNN_OK;
+    if (done[i].k == (const void*)kernel && done[i].dev == dev) return B200RNN_OK;
   B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (ndone < 128) done[ndone++] = (const void*)kernel;
+  if (ndone < 256) done[ndone++] = Done{(const void*)kernel, dev};
   return B200RNN_OK;
 }
 
@@ -753,15 +565,16 @@ template <typename K>
 int max_active_clusters(K kernel, int C, int NT, size_t smem) {
   struct Entry {
     const void* k;
-    int n;
+    int dev, n;
   };
   static std::mutex mu;
-  static Entry cache[128];
+  static Entry cache[256];
   static int ncache = 0;
+  const int dev = current_device();
   {
     std::lock_guard<std::mutex> lk(mu);
     for (int i = 0; i < ncache; ++i)
-      if (cache[i].k == (const void*)kernel) return cache[i].n;
+      if (cache[i].k == (const void*)kernel && cache[i].dev == dev) return cache[i].n;
   }
   if (prepare_kernel(kernel, smem) != B200RNN_OK) return 0;
   cudaLaunchConfig_t cfg = {};
@@ -781,7 +594,7 @@ int max_active_clusters(K kernel, int C, int NT, size_t smem) {
     n = 0;
   }
   std::lock_guard<std::mutex> lk(mu);
-  if (ncache < 128) cache[ncache++] = Entry{(const void*)kernel, n};
+  if (ncache < 256) cache[ncache++] = Entry{(const void*)kernel, dev, n};
   return n;
 }
 
@@ -824,9 +637,18 @@ bool try_bwd(RecBwdParams& p, cudaStream_t s, bool force, int* rc) {
   return true;
 }
 
-int env_variant(const char* name) {
+int env_variant(const char* name, int dflt) {
   const char* v = getenv(name);
-  return v ? atoi(v) : 0;
+  return v ? atoi(v) : dflt;
+}
+
+// Where the tcgen05 recurrence beats the FFMA kernel on a B200 (same-box A/B, profiles/README.md "dispatch table"):
+// the FFMA kernel needs ceil(B/4) clusters of C CTAs and is latency-bound per step whatever the batch, the tensor-core
+// kernel packs up to 16 rows per cluster but pays an 8-CTA all-to-all per step that grows with the rows per cluster.
+bool rec_tc_preferred(const RecFwdParams& p) {
+  if (p.lengths != nullptr || p.D != 1) return false;
+  if (p.mode == B200RNN_GRU && p.H == 256) return p.B <= 48;
+  return false;
 }
 
 }  // namespace
@@ -840,30 +662,14 @@ int rec_bwd_max_slices(int B) { return (B + 3) / 4; }
 int launch_rec_fwd(const RecFwdParams& p, cudaStream_t s) {
   int rc = B200RNN_OK;
   if (p.B <= 0 || p.T <= 0) return rc;
-  static const int variant = env_variant("B200RNN_FWD_VARIANT");  // tuning knob for the GRU H=256 forward
-  static const int rec_tc = env_variant("B200RNN_REC_TC");
-  if (rec_tc && launch_rec_fwd_tc(p, s, &rc)) return rc;
+  // Batch-size-aware choice between the FFMA kernel and the tcgen05 recurrence (rnn_rec_tc.cu): see rec_tc_preferred().
+  // B200RNN_REC_TC=1 / =0 forces it on / off (A/B runs, tests/test_gpu_tc_rec.py).
+  static const int rec_tc = env_variant("B200RNN_REC_TC", -1);
+  if ((rec_tc == 1 || (rec_tc < 0 && rec_tc_preferred(p))) && launch_rec_fwd_tc(p, s, &rc)) return rc;
+  // One tuned config per shape (B200, round-1/2 A/B runs in profiles/README.md) plus a wider-batch fallback that runs
+  // in several waves when the batch needs more clusters than fit the chip.
   if (p.mode == B200RNN_GRU && p.H == 256) {
-    if (variant == 1) {
-      if (try_fwd<B200RNN_GRU, 256, 4, 4, 32, 8, 1>(p, s, false, &rc)) return rc;
-    } else if (variant == 2) {
-      if (try_fwd<B200RNN_GRU, 256, 4, 4, 8, 2, 0>(p, s, false, &rc)) return rc;
-    } else if (variant == 3) {
-      try_fwd<B200RNN_GRU, 256, 8, 8, 32, 4, 1>(p, s, true, &rc);
-      return rc;
-    } else if (variant == 4) {  // 128-thread CTAs, two per SM: two independent recurrences overlap their latency
-      if (try_fwd<B200RNN_GRU, 256, 8, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
-    } else if (variant == 6 && !p.lengths) {  // EXPERIMENTAL: z gate block in tensor memory (rec_fwd_tm_kernel)
-      using Tm = TmCfg<256, 4, 4, 16, 4>;
-      auto k = rec_fwd_tm_kernel<256, 4, 4, 16, 4>;
-      const int nslices = (p.B + 3) / 4;
-      if (nslices * p.D <= max_active_clusters(k, 4, Tm::NT, Tm::SMEM))
-        return launch_clustered(k, p, nslices, nslices * p.D, 4, Tm::NT, Tm::SMEM, s, PROF_REC_FWD);
-    } else if (variant == 5) {  // two gate blocks in registers: halves the shared-memory weight traffic per step
-      if (try_fwd<B200RNN_GRU, 256, 4, 4, 16, 4, 2>(p, s, false, &rc)) return rc;
-    } else {  // default: measured fastest on B200 (232 us for B=128, T=120)
-      if (try_fwd<B200RNN_GRU, 256, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
-    }
+    if (try_fwd<B200RNN_GRU, 256, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;  // 232 us at B=128, T=120
     try_fwd<B200RNN_GRU, 256, 8, 8, 32, 4, 1>(p, s, true, &rc);
     return rc;
   }
@@ -878,7 +684,6 @@ int launch_rec_fwd(const RecFwdParams& p, cudaStream_t s) {
     return rc;
   }
   if (p.mode == B200RNN_LSTM && p.H == 128) {
-    if (variant == 4 && try_fwd<B200RNN_LSTM, 128, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
     if (try_fwd<B200RNN_LSTM, 128, 2, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
     try_fwd<B200RNN_LSTM, 128, 4, 8, 16, 2, 1>(p, s, true, &rc);
     return rc;
@@ -892,30 +697,24 @@ int launch_rec_bwd(RecBwdParams& p, cudaStream_t s) {
   int rc = B200RNN_OK;
   if (p.B <= 0 || p.T <= 0) return rc;
   // K across all 32 lanes with 8 units per lane halves the redundant reads of the [BS][G*H] gradient vector, which
-  // (not the weights) dominates the shared-memory traffic of the backward contraction: 303 -> 278 us (GRU H=256);
-  // B200RNN_BWD_VARIANT=1 selects the previous 16-lane split for comparison
-  static const int bvariant = env_variant("B200RNN_BWD_VARIANT");
+  // (not the weights) dominates the shared-memory traffic of the backward contraction: 303 -> 278 us (GRU H=256)
   if (p.mode == B200RNN_GRU && p.H == 256) {
-    if (bvariant != 1 && try_bwd<B200RNN_GRU, 256, 4, 4, 32, 8, 1>(p, s, false, &rc)) return rc;
-    if (try_bwd<B200RNN_GRU, 256, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    if (try_bwd<B200RNN_GRU, 256, 4, 4, 32, 8, 1>(p, s, false, &rc)) return rc;
     try_bwd<B200RNN_GRU, 256, 8, 8, 32, 4, 1>(p, s, true, &rc);
     return rc;
   }
   if (p.mode == B200RNN_GRU && p.H == 128) {
-    if (bvariant != 1 && try_bwd<B200RNN_GRU, 128, 2, 4, 32, 8, 1>(p, s, false, &rc)) return rc;
-    if (try_bwd<B200RNN_GRU, 128, 2, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    if (try_bwd<B200RNN_GRU, 128, 2, 4, 32, 8, 1>(p, s, false, &rc)) return rc;
     try_bwd<B200RNN_GRU, 128, 4, 8, 32, 4, 1>(p, s, true, &rc);
     return rc;
   }
   if (p.mode == B200RNN_LSTM && p.H == 256) {
-    if (bvariant != 1 && try_bwd<B200RNN_LSTM, 256, 4, 4, 32, 8, 1>(p, s, false, &rc)) return rc;
-    if (try_bwd<B200RNN_LSTM, 256, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    if (try_bwd<B200RNN_LSTM, 256, 4, 4, 32, 8, 1>(p, s, false, &rc)) return rc;
     try_bwd<B200RNN_LSTM, 256, 8, 8, 32, 4, 1>(p, s, true, &rc);
     return rc;
   }
   if (p.mode == B200RNN_LSTM && p.H == 128) {
-    if (bvariant != 1 && try_bwd<B200RNN_LSTM, 128, 2, 4, 32, 8, 1>(p, s, false, &rc)) return rc;
-    if (try_bwd<B200RNN_LSTM, 128, 2, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    if (try_bwd<B200RNN_LSTM, 128, 2, 4, 32, 8, 1>(p, s, false, &rc)) return rc;
     try_bwd<B200RNN_LSTM, 128, 4, 8, 32, 4, 1>(p, s, true, &rc);
     return rc;
   }

@@ -517,26 +517,32 @@ __global__ void __launch_bounds__(TC_NT, 1) rec_fwd_tc_kernel(const RecFwdParams
 template <typename K>
 int tc_prepare(K kernel, size_t smem) {
   static std::mutex mu;
-  static const void* done[16];
+  static const void* done[64];
+  static int done_dev[64];
   static int ndone = 0;
+  const int dev = current_device();
   std::lock_guard<std::mutex> lk(mu);
   for (int i = 0; i < ndone; ++i)
-    if (done[i] == (const void*)kernel) return B200RNN_OK;
+    if (done[i] == (const void*)kernel && done_dev[i] == dev) return B200RNN_OK;
   B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (ndone < 16) done[ndone++] = (const void*)kernel;
+  if (ndone < 64) {
+    done[ndone] = (const void*)kernel;
+    done_dev[ndone++] = dev;
+  }
   return B200RNN_OK;
 }
 
 template <typename K>
 int tc_capacity(K kernel, int C, size_t smem) {
   static std::mutex mu;
-  static const void* keys[16];
-  static int vals[16];
+  static const void* keys[64];
+  static int vals[64], devs[64];
   static int n = 0;
+  const int dev = current_device();
   {
     std::lock_guard<std::mutex> lk(mu);
     for (int i = 0; i < n; ++i)
-      if (keys[i] == (const void*)kernel) return vals[i];
+      if (keys[i] == (const void*)kernel && devs[i] == dev) return vals[i];
   }
   if (tc_prepare(kernel, smem) != B200RNN_OK) return 0;
   cudaLaunchConfig_t cfg = {};
@@ -556,8 +562,9 @@ int tc_capacity(K kernel, int C, size_t smem) {
     cap = 0;
   }
   std::lock_guard<std::mutex> lk(mu);
-  if (n < 16) {
+  if (n < 64) {
     keys[n] = (const void*)kernel;
+    devs[n] = dev;
     vals[n++] = cap;
   }
   return cap;

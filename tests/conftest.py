@@ -19,11 +19,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session", autouse=True)
 def _built_library():
     """Every test run starts from a built C-ABI library (nvcc cross-compiles sm_100a without a GPU)."""
-    lib = os.path.join(PKG, "lib", "libb200rnn.so")
-    if not os.path.exists(lib):
-        import __graft_entry__
+    # build() unconditionally (an incremental `make`: seconds when nothing changed), so the tests always run the
+    # binary the tree's sources produce - never a stale pre-built one that merely travelled with the snapshot
+    import __graft_entry__
 
-        __graft_entry__.build()
+    __graft_entry__.build()
+    lib = os.path.join(PKG, "lib", "libb200rnn.so")
     assert os.path.exists(lib), "libb200rnn.so missing and build() did not produce it"
     yield
 

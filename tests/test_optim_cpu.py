@@ -46,7 +46,8 @@ def test_parameters_and_gradients_live_in_the_flat_buffers():
         lo, hi = g.flat_p.data_ptr(), g.flat_p.data_ptr() + 4 * g.flat_p.numel()
         off = 0
         for p in g.params:
-            assert lo <= p.data_ptr() < hi and p.data_ptr() == lo + 4 * off   # packed in order, no gaps
+            off = (off + 63) // 64 * 64     # packed in order, every view on a 256-byte boundary of the flat buffer
+            assert lo <= p.data_ptr() < hi and p.data_ptr() == lo + 4 * off
             assert p.grad.data_ptr() == g.flat_g.data_ptr() + 4 * off
             off += p.numel()
         assert off == g.flat_p.numel()
@@ -69,6 +70,7 @@ def test_frozen_parameters_are_left_out_and_step_has_no_cpu_path():
     m.fc.weight.requires_grad = False
     opt = b200rnn.FlatAdamW.like_reference(m, lr=1e-3)
     assert all(id(m.fc.weight) != id(p) for g in opt.groups for p in g.params)
-    assert sum(g.flat_p.numel() for g in opt.groups) == sum(p.numel() for p in m.parameters() if p.requires_grad)
+    assert (sum(p.numel() for g in opt.groups for p in g.params) ==
+            sum(p.numel() for p in m.parameters() if p.requires_grad))
     with pytest.raises(b200rnn.B200RNNError, match="no CPU path"):
         opt.step()      # the update is a CUDA kernel (b200rnn_adamw); there is no CPU fallback

@@ -316,6 +316,111 @@ def _time_module_train(kind: str, dev, iters: int = 20, warmup: int = 5) -> dict
             "mode": mode + ", train mode (dropout on), dx computed, full model incl. loss"}
 
 
+def _parity_check(model, fused, dev) -> dict:
+    """Checker leg (not timed, not shipped): the benched object at the benched size against the CPU oracle.
+
+    ``FusedFuseStep.features`` + logits in ``eval()`` (dropout streams cannot match bit for bit in train mode) on one
+    B=128 batch vs ``oracle.ref_models.RefFusion`` (stock torch.nn.GRU/LSTM on CPU = the reference's arithmetic,
+    fuse_net_whole.py:336-374) with the same state_dict. tests/test_gpu_fuse_parity.py runs the full three-step
+    version (loss, Adam update, train mode with p=0, all-grads variant).
+    """
+    from oracle import ref_models
+
+    ref = ref_models.RefFusion(**FUSE_ARGS)
+    ref.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()})
+    ref.eval()
+    audio, text, labels = _synthetic(B_PER_GPU, 4321)
+    was_training = model.training
+    model.eval()
+    try:
+        with torch.no_grad():
+            tf_r, af_r = ref.pretrained_feature_tensors(audio, text)
+            w = ref.fc_final[0].weight
+            logits_r = torch.cat((tf_r, af_r), dim=1) @ w.t()
+            loss_r = ref_models.ref_fusion_loss(tf_r, af_r, labels, ref)
+            tf_m, af_m = fused.features(__import__("b200rnn").FuseBatch(audio.to(dev), text.to(dev)))
+            torch.cuda.synchronize()
+            tf_m, af_m = tf_m.cpu(), af_m.cpu()
+            logits_m = torch.cat((tf_m, af_m), dim=1) @ w.t()
+            loss_m = ref_models.ref_fusion_loss(tf_m, af_m, labels, ref)
+    finally:
+        model.train(was_training)
+    out = {
+        "against": "oracle.ref_models.RefFusion (stock torch.nn.GRU/LSTM, CPU), same weights, eval(), B=128 T=120/30",
+        "features_max_abs": max((tf_m - tf_r).abs().max().item(), (af_m - af_r).abs().max().item()),
+        "logits_max_abs": (logits_m - logits_r).abs().max().item(),
+        "loss_abs": abs(loss_m.item() - loss_r.item()),
+        "tolerance_logits": 1e-4,
+    }
+    out["ok"] = bool(out["logits_max_abs"] <= 1e-4 and out["features_max_abs"] <= 1e-4)
+    return out
+
+
+def _cudnn_comparator(dev, iters: int = 20, warmup: int = 5) -> dict:
+    """Same-box yardstick: stock torch.nn.GRU / nn.LSTM on CUDA = cuDNN's RNN, same shapes as the
+    encoders of the fuse step (and of BASELINE c2/c3), forward and forward+backward, CUDA-graph replay, next to this
+    library's modules timed the same way. A library call - reported, not part of any headline number."""
+    import b200rnn
+
+    shapes = [("gru_fuse_B128_T120_I256_H256", "gru", 128, 120, 256, 256, False),
+              ("bilstm_fuse_B128_T30_I1024_H128", "lstm", 128, 30, 1024, 128, True),
+              ("gru_c2_B64_T120_I256_H256", "gru", 64, 120, 256, 256, False),
+              ("bilstm_c3_B64_T30_I1024_H256", "lstm", 64, 30, 1024, 256, True)]
+    out = {}
+
+    def timed(fn):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        for _ in range(warmup):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        del g
+        return e0.elapsed_time(e1) / iters
+
+    for name, kind, B, T, I, H, bi in shapes:
+        torch.manual_seed(0)
+        cls = torch.nn.GRU if kind == "gru" else torch.nn.LSTM
+        stock = cls(I, H, num_layers=2, bidirectional=bi, batch_first=True).to(dev)
+        mine = b200rnn.from_torch(stock).to(dev)
+        x = torch.randn(B, T, I, device=dev)
+        xg = x.clone().requires_grad_(True)
+        row = {}
+        for label, mod in (("cudnn", stock), ("b200rnn", mine)):
+            mod.eval()
+            with torch.no_grad():
+                row[label + "_fwd_ms"] = timed(lambda: mod(x))
+            mod.train()   # dropout = 0: train mode only switches the saved-for-backward stores on
+
+            def fb():
+                y = mod(xg)[0]
+                y.sum().backward()
+
+            try:
+                row[label + "_fwd_bwd_ms"] = timed(fb)
+            except Exception as exc:  # noqa: BLE001
+                row[label + "_fwd_bwd_ms"] = None
+                _log(f"cudnn comparator {name} {label} fwd+bwd failed: {type(exc).__name__}: {exc}")
+                torch.cuda.synchronize()
+        out[name] = row
+    out["note"] = ("stock torch.nn.GRU/LSTM(...).cuda() (cuDNN RNN, fp32, TF32 off by torch default) vs b200rnn modules; "
+                   "2 layers, batch_first, CUDA-graph replay, dropout 0; fwd = eval no_grad, fwd_bwd = y.sum().backward()")
+    return out
+
+
 def run_ours(args) -> None:
     import b200rnn
     from b200rnn import _lib
@@ -373,6 +478,11 @@ def run_ours(args) -> None:
         return out
 
     _log(f"rank {rank}/{world}: model built, host cores usable {usable_cores()} (os.cpu_count {os.cpu_count()})")
+    parity = None
+    if rank == 0 and fused is not None and not args.no_parity:
+        parity = _parity_check(model, fused, dev)
+        _log("parity vs CPU oracle: " + json.dumps(parity))
+    _barrier()
     # ---- eager warm-up (also counts this library's launches per step) -------------------------------
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -530,6 +640,7 @@ def run_ours(args) -> None:
 
     if rank == 0:
         line["clocks"] = clocks
+        line["parity"] = parity
         # ---- roofline of the dominant kernel: forward GRU recurrence (2 launches per step) --------------
         hbm_peak, peak_src = _peaks()
         x_a = dev_in[0][0]
@@ -581,6 +692,7 @@ def run_ours(args) -> None:
             extra["c2_audio_gru_whole_train_B64_T120"] = _time_module_train("c2", dev)
             extra["c3_text_bilstm_whole_train_B64_T30_H256"] = _time_module_train("c3", dev)
             extra["c4_finetune_all_grads_B128"] = _finetune_variant(dev)
+            extra["cudnn_comparator"] = _cudnn_comparator(dev)
         line["extra"] = extra
         _log("extras done: " + json.dumps(extra)[:400])
         # ---- CPU baseline on this box's host cores (bounded sample) -----------------------------------
@@ -676,6 +788,7 @@ def main() -> None:
     ap.add_argument("--generic-head", action="store_true",
                     help="run the dense shells / loss / Adam as PyTorch ops instead of the fused shell kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing parity check against the CPU oracle")
     ap.add_argument("--quick", action="store_true", help="skip the secondary module timings")
     args = ap.parse_args()
     _protect_stdout()

@@ -450,12 +450,15 @@ def run_ours(args) -> None:
     b200rnn.broadcast_parameters(model)
     model.train()
     criterion = b200rnn.MyLoss(text_hidden_dims=H_TEXT)
-    bucket = b200rnn.GradBucket(model)
-    fused = None
+    fused, bucket = None, None
     if args.generic_head:   # PyTorch shells around the encoders: attention, MLP heads, MyLoss, autograd, torch Adam
+        bucket = b200rnn.GradBucket(model)
         opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=LR, capturable=True)
-    else:                   # the same step on the library's fused shell kernels (b200rnn.FusedFuseStep)
-        fused = b200rnn.FusedFuseStep(model, lr=LR, bucket=bucket)
+    else:                   # the same step on the library's fused head kernel (b200rnn.FusedFuseStep): the gradient
+        #                     exchange across ranks happens inside that kernel over NVLink peer stores ("peer") or,
+        #                     with --exchange nccl, as a separate ncclAllReduce + Adam launch
+        fused = b200rnn.FusedFuseStep(model, lr=LR, exchange=args.exchange)
+        _log(f"rank {rank}: gradient exchange = {fused.exchange}")
 
     # ---- synthetic shards: rank r owns its own 128 sequences of the global batch (weak scaling) -------
     host = [_synthetic(B_PER_GPU, 1234 + 100 * rank + i) for i in range(N_ROTATE)]
@@ -628,7 +631,8 @@ def run_ours(args) -> None:
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": _config(n_gpus),
         "cuda_graph": bool(use_graph),
-        "shells": "fused kernels (b200rnn.FusedFuseStep)" if fused is not None else "PyTorch ops",
+        "shells": "fused head kernel (b200rnn.FusedFuseStep)" if fused is not None else "PyTorch ops",
+        "grad_exchange": (fused.exchange if fused is not None else ("nccl" if world > 1 else "none")),
         "gpu_launches": int(launches_per_step * K),
         "gpu_launches_per_step": int(launches_per_step),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
@@ -705,10 +709,10 @@ def run_ours(args) -> None:
                           f"(oracle/ref_models.py on stock torch.nn CPU kernels, {cores} threads); with the reference's "
                           f"list->tensor conversion (fuse_net_whole.py:343) it is {v2:.1f} seq/s ({ms2:.0f} ms/step)"}
         _emit(line)
-    _teardown(graphs, e2e_graphs, world)
+    _teardown(graphs, e2e_graphs, world, fused)
 
 
-def _teardown(graphs, e2e_graphs, world: int) -> None:
+def _teardown(graphs, e2e_graphs, world: int, fused=None) -> None:
     """Normal interpreter exit (the driver's exit hook records which .so files this process loaded).
 
     Round 1 left with os._exit(0) because a 2-rank run once hung in destroy_process_group while captured graphs still
@@ -733,6 +737,8 @@ def _teardown(graphs, e2e_graphs, world: int) -> None:
     graphs.clear()
     e2e_graphs.clear()
     torch.cuda.synchronize()
+    if fused is not None:
+        fused.close()          # unmap the peer exchange buffers (barrier inside)
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
@@ -790,6 +796,8 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing parity check against the CPU oracle")
     ap.add_argument("--quick", action="store_true", help="skip the secondary module timings")
+    ap.add_argument("--exchange", choices=["auto", "peer", "nccl"], default="auto",
+                    help="data-parallel gradient exchange of the fused step: in-kernel NVLink peer stores or NCCL")
     args = ap.parse_args()
     _protect_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -35,9 +35,18 @@ SYMBOLS = (
     "b200rnn_fuse_loss_grad",
     "b200rnn_adam",
     "b200rnn_adamw",
+    "b200rnn_fuse_head",
+    "b200rnn_fuse_head_scratch_floats",
+    "b200rnn_comm_bytes",
+    "b200rnn_comm_create",
+    "b200rnn_comm_open",
+    "b200rnn_comm_close",
+    "b200rnn_comm_destroy",
     "b200rnn_profile",
     "b200rnn_profile_read",
 )
+COMM_MAX_WORLD = 8
+IPC_HANDLE_BYTES = 64
 
 
 class Desc(ctypes.Structure):
@@ -55,6 +64,39 @@ class Desc(ctypes.Structure):
         ("dropout_p", c_float),
         ("flags", c_uint32),
     ]
+
+
+class FuseHeadArgs(ctypes.Structure):
+    """``b200rnn_fuse_head_args`` (include/b200rnn.h), field for field."""
+
+    _fields_ = [
+        ("struct_bytes", c_uint32),
+        ("B", c_int32), ("T", c_int32), ("Ht", c_int32), ("Ha", c_int32),
+        ("n_states", c_int32),
+        ("training", c_int32),
+        ("p", c_float),
+        ("regression", c_int32),
+        ("accumulate", c_int32),
+        ("do_adam", c_int32),
+        ("world", c_int32), ("rank", c_int32),
+        ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("grad_scale", c_float),
+        ("rng_consume", c_uint64),
+        ("seq_st", c_int64), ("seq_sb", c_int64),
+        ("seq", c_void_p), ("h_n", c_void_p), ("w_att", c_void_p), ("b_att", c_void_p),
+        ("ctx_in", c_void_p), ("ctx_out", c_void_p),
+        ("w_t", c_void_p), ("b_t", c_void_p), ("pooled", c_void_p), ("w_a", c_void_p), ("b_a", c_void_p),
+        ("rng_state", c_void_p),
+        ("text_feature", c_void_p), ("audio_feature", c_void_p),
+        ("W", c_void_p), ("w_modal", c_void_p), ("labels", c_void_p),
+        ("out", c_void_p), ("loss", c_void_p), ("dw_part", c_void_p), ("dw", c_void_p), ("ticket", c_void_p),
+        ("adam_m", c_void_p), ("adam_v", c_void_p), ("adam_step", c_void_p),
+        ("comm_step", c_void_p),
+        ("comm_buf", c_void_p * 8),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.struct_bytes = ctypes.sizeof(FuseHeadArgs)
 
 
 class B200RNNError(RuntimeError):
@@ -137,6 +179,20 @@ def load() -> ctypes.CDLL:
     lib.b200rnn_adamw.restype = c_int
     lib.b200rnn_adamw.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
                                   c_float, c_float, c_float, c_int, c_void_p]
+    lib.b200rnn_fuse_head.restype = c_int
+    lib.b200rnn_fuse_head.argtypes = [POINTER(FuseHeadArgs), c_void_p]
+    lib.b200rnn_fuse_head_scratch_floats.restype = c_size_t
+    lib.b200rnn_fuse_head_scratch_floats.argtypes = [c_int, c_int, c_int, c_int]
+    lib.b200rnn_comm_bytes.restype = c_size_t
+    lib.b200rnn_comm_bytes.argtypes = []
+    lib.b200rnn_comm_create.restype = c_int
+    lib.b200rnn_comm_create.argtypes = [POINTER(c_void_p), POINTER(ctypes.c_ubyte)]
+    lib.b200rnn_comm_open.restype = c_int
+    lib.b200rnn_comm_open.argtypes = [POINTER(ctypes.c_ubyte), POINTER(c_void_p)]
+    lib.b200rnn_comm_close.restype = c_int
+    lib.b200rnn_comm_close.argtypes = [c_void_p]
+    lib.b200rnn_comm_destroy.restype = c_int
+    lib.b200rnn_comm_destroy.argtypes = [c_void_p]
     lib.b200rnn_profile.restype = c_int
     lib.b200rnn_profile.argtypes = [c_int]
     lib.b200rnn_profile_read.restype = c_int

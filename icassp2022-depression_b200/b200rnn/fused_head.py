@@ -1,11 +1,11 @@
 """Fused model-shell kernels of the fuse step, Python side.
 
-``FusedFuseStep`` runs one ``fuse_net_whole`` train step in reference semantics (fuse_net_whole.py:421-465: encoders
-under no_grad with train-mode dropout, only ``fc_final.0.weight`` trainable, ``MyLoss``, Adam) with ~20 launches of
-this library instead of ~90 framework launches: attention pooling, the two Dropout-Linear-ReLU-Dropout heads, the
-two-head cross entropy with its weight gradient and the fused softmax output, and the Adam update are one kernel each.
-It is a drop-in for ``pretrained_feature`` + ``forward`` + ``MyLoss`` + ``backward`` + ``optimizer.step`` when the
-model is the classification ``fusion_net`` with two classes; anything else keeps the generic PyTorch path.
+``FusedFuseStep`` runs one fuse train step in reference semantics (fuse_net_whole.py:421-465: encoders under no_grad
+with train-mode dropout, only ``fc_final.0.weight`` trainable, ``MyLoss``, Adam): the two encoder calls plus ONE
+launch (``b200rnn_fuse_head``) for attention pooling, both Dropout-Linear-ReLU-Dropout heads, the model output, the
+two-head loss, its weight gradient, the data-parallel gradient sum over NVLink and the Adam update. It is a drop-in
+for ``pretrained_feature`` + ``forward`` + ``MyLoss`` + ``backward`` + ``optimizer.step`` of both the classification
+and the regression ``fusion_net``. The single-purpose kernels (``attention_pool``, ``mlp_dropout``) stay available.
 """
 from __future__ import annotations
 
@@ -68,67 +68,179 @@ def mlp_dropout(x: torch.Tensor, linear: torch.nn.Linear, p: float, training: bo
 
 
 class FusedFuseStep:
-    """One reference-semantics ``fuse_net_whole`` train step on fused kernels (see module docstring)."""
+    """One reference-semantics fuse train step (fuse_net_whole.py:421-465 / Regression/fuse_net.py:373-412) on fused
+    kernels: encoders under no_grad with train-mode dropout, only ``fc_final.0.weight`` trainable, ``MyLoss``, Adam.
 
-    def __init__(self, model, lr: float = 8e-6, betas=(0.9, 0.999), eps: float = 1e-8, bucket=None):
-        if getattr(model, "regression", False) or model.num_classes != 2:
-            raise NotImplementedError("FusedFuseStep covers the 2-class classification fusion_net")
+    After the two encoder calls everything - attention pooling, both Dropout-Linear-ReLU-Dropout heads, the model
+    output, the two-head loss, ``d fc_final.0.weight``, the data-parallel gradient sum and the Adam update - is ONE
+    launch of ``b200rnn_fuse_head``. Both flavours are covered: the 2-class classification ``fusion_net`` (Softmax
+    output, cross entropy) and the regression one (sigmoid ``modal_attn`` gate + ReLU output, SmoothL1, one output).
+
+    Data parallel (``torch.distributed`` initialised, world > 1): ``exchange="peer"`` (default when CUDA IPC peer
+    mapping works) sums the 3 KB gradient inside the same kernel through peer-mapped buffers over NVLink
+    (:class:`b200rnn.dp.PeerComm`); ``exchange="nccl"`` keeps the separate ``all_reduce`` + ``b200rnn_adamw`` launches.
+    """
+
+    def __init__(self, model, lr: float = 8e-6, betas=(0.9, 0.999), eps: float = 1e-8, bucket=None,
+                 process_group=None, exchange: str = "auto"):
+        import torch.distributed as dist
+
+        self.regression = bool(getattr(model, "regression", False))
+        self.C = 1 if self.regression else 2
+        if model.num_classes != self.C:
+            raise NotImplementedError("FusedFuseStep covers the 2-class classification fusion_net and the 1-output "
+                                      f"regression fusion_net (got num_classes={model.num_classes})")
         self.model = model
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         w = model.fc_final[0].weight
         _require_cuda(("model (fc_final.0.weight)", w))
         dev = w.device
         self.w = w
-        self.bucket = bucket  # b200rnn.dp.GradBucket over the trainable parameter(s), or None (single process)
-        self.grad = bucket.flat if bucket is not None else torch.zeros(w.numel(), device=dev)
-        assert self.grad.numel() == w.numel(), "reference semantics: only fc_final.0.weight is trainable"
-        self.m = torch.zeros(w.numel(), device=dev)
-        self.v = torch.zeros(w.numel(), device=dev)
+        self.F = model.text_hidden_dims + model.audio_hidden_dims
+        n = self.C * self.F
+        assert w.numel() == n and w.is_contiguous()
+        self.group = process_group if process_group is not None else getattr(bucket, "group", None)
+        self.world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(self.group) if self.world > 1 else 0
+        self.dw = torch.zeros((n + 1 + 3) // 4 * 4, device=dev)     # gradient, then this rank's loss
+        self.grad = self.dw[:n]
+        self.m = torch.zeros(n, device=dev)
+        self.v = torch.zeros(n, device=dev)
         self.step_count = torch.zeros((), device=dev)
         self.loss = torch.zeros((), device=dev)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._dw_part = None
         self.rng_hdr = torch.zeros(2, dtype=torch.int64, device=dev)
         self.rng_state = torch.tensor([(torch.initial_seed() * 2654435761 + 12345) & 0x7FFFFFFFFFFFFFFF, 0],
                                       dtype=torch.int64, device=dev)
+        self.comm = None
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        self.exchange = "none"
+        if self.world > 1:
+            self.exchange = "nccl"
+            if exchange in ("auto", "peer"):
+                try:
+                    from .dp import PeerComm
+
+                    self.comm = PeerComm(dev, self.group)
+                    self.exchange = "peer"
+                except Exception:
+                    if exchange == "peer":
+                        raise
+                # every rank must take the same path: fall back together if any rank could not map its peers
+                ok = torch.tensor([1 if self.comm is not None else 0], device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+                if int(ok.item()) == 0:
+                    if self.comm is not None:
+                        self.comm.close()
+                    self.comm, self.exchange = None, "nccl"
+
+    def close(self) -> None:
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None
+
+    def _encoders(self, batch: FuseBatch):
+        m = self.model
+        seq, h_n, _ = rnn_forward_fused(batch.text.permute(1, 0, 2), m.lstm_net._flat_weights, m.lstm_net._config(),
+                                        m.lstm_net._rng_state)
+        pooled = m.lstm_net_audio.forward_ln_sum(batch.audio, None if self.regression else m.ln)
+        return seq, h_n.contiguous(), pooled
+
+    def _args(self, seq, h_n, pooled, tf, af) -> "_lib.FuseHeadArgs":
+        m = self.model
+        T, B, H2 = seq.shape
+        assert seq.stride(2) == 1 and pooled.is_contiguous()
+        att, lt, la = m.attention_layer[0], m.fc_out[1], m.fc_audio[1]
+        _require_cuda(("attention weight", att.weight), ("fc_out weight", lt.weight), ("fc_audio weight", la.weight))
+        return _lib.FuseHeadArgs(
+            B=B, T=T, Ht=m.text_hidden_dims, Ha=m.audio_hidden_dims, n_states=h_n.shape[0],
+            training=int(m.training), p=float(m.dropout), regression=int(self.regression),
+            seq_st=seq.stride(0), seq_sb=seq.stride(1), seq=seq.data_ptr(), h_n=h_n.data_ptr(),
+            w_att=att.weight.data_ptr(), b_att=att.bias.data_ptr(), w_t=lt.weight.data_ptr(), b_t=lt.bias.data_ptr(),
+            pooled=pooled.data_ptr(), w_a=la.weight.data_ptr(), b_a=la.bias.data_ptr(),
+            text_feature=tf.data_ptr(), audio_feature=af.data_ptr())
 
     @torch.no_grad()
     def features(self, batch: FuseBatch):
+        """(text_feature [B,Ht], audio_feature [B,Ha]) = ``model.pretrained_feature(batch)`` (fuse_net_whole.py:336-366)
+        with the head stage of ``b200rnn_fuse_head`` only (no loss, no update)."""
         m = self.model
         lib = _lib.load()
-        seq, h_n, _ = rnn_forward_fused(batch.text.permute(1, 0, 2), m.lstm_net._flat_weights, m.lstm_net._config(),
-                                        m.lstm_net._rng_state)
-        ctx = attention_pool(seq, h_n, m.attention_layer)
-        training, p = m.training, m.dropout
-        if training and p > 0:
-            B = batch.text.shape[0]
-            consume = (B * max(m.text_hidden_dims, m.audio_hidden_dims) + 3) // 4
-            _lib.check(lib.b200rnn_rng_next(self.rng_hdr.data_ptr(), self.rng_state.data_ptr(), consume, _stream()),
-                       "b200rnn_rng_next")
-        text_feature = mlp_dropout(ctx, m.fc_out[1], p, training, self.rng_hdr, 0)
-        pooled = m.lstm_net_audio.forward_ln_sum(batch.audio, m.ln)
-        audio_feature = mlp_dropout(pooled, m.fc_audio[1], p, training, self.rng_hdr, 2)
-        return text_feature, audio_feature
+        _require_cuda(("batch.audio", batch.audio), ("batch.text", batch.text))
+        dev = batch.text.device
+        seq, h_n, pooled = self._encoders(batch)
+        B = seq.shape[1]
+        tf = torch.empty(B, m.text_hidden_dims, device=dev)
+        af = torch.empty(B, m.audio_hidden_dims, device=dev)
+        a = self._args(seq, h_n, pooled, tf, af)
+        with _on(dev):
+            if m.training and m.dropout > 0:
+                consume = (B * max(m.text_hidden_dims, m.audio_hidden_dims) + 3) // 4
+                _lib.check(lib.b200rnn_rng_next(self.rng_hdr.data_ptr(), self.rng_state.data_ptr(), consume,
+                                                _stream(dev)), "b200rnn_rng_next")
+                a.rng_state = self.rng_hdr.data_ptr()
+            rc = lib.b200rnn_fuse_head(ctypes.byref(a), _stream(dev))
+        _lib.check(rc, "b200rnn_fuse_head")
+        return tf, af
 
     @torch.no_grad()
     def __call__(self, batch: FuseBatch, labels: torch.Tensor):
-        """Runs the step; returns (probs [B,2], loss scalar tensor)."""
+        """Runs the step; returns (model output [B,2] probabilities / [B,1] prediction, loss scalar tensor)."""
         lib = _lib.load()
         m = self.model
         _require_cuda(("labels", labels), ("batch.audio", batch.audio), ("batch.text", batch.text))
-        tf, af = self.features(batch)
-        B = tf.shape[0]
-        # the kernel reads `const int64_t labels[B]`: anything else (int32 from numpy, float, a strided view) would be
-        # silently misread, so it is converted here; the values must be class indices 0/1 (checked on the device)
-        if labels.dtype != torch.int64 or not labels.is_contiguous():
-            labels = labels.to(torch.int64).contiguous()
+        dev = batch.text.device
+        seq, h_n, pooled = self._encoders(batch)
+        B = seq.shape[1]
+        # the kernel reads `const int64_t labels[B]` (classification) / `const float labels[B]` (regression): anything
+        # else (int32 from numpy, a strided view) would be silently misread, so it is converted here; class indices
+        # outside {0,1} poison the loss with NaN on the device
+        want = torch.float32 if self.regression else torch.int64
+        if labels.dtype != want or not labels.is_contiguous():
+            labels = labels.to(want).contiguous()
         if labels.numel() != B:
             raise ValueError(f"FusedFuseStep: {labels.numel()} labels for a batch of {B}")
-        probs = torch.empty(B, 2, dtype=torch.float32, device=tf.device)
-        _lib.check(lib.b200rnn_fuse_loss_grad(tf.data_ptr(), tf.shape[1], af.data_ptr(), af.shape[1], labels.data_ptr(), B,
-                                              self.w.data_ptr(), self.grad.data_ptr(), 0, self.loss.data_ptr(),
-                                              probs.data_ptr(), _stream()), "b200rnn_fuse_loss_grad")
-        if self.bucket is not None:
-            self.bucket.allreduce()
-        _lib.check(lib.b200rnn_adam(self.w.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                                    self.step_count.data_ptr(), self.w.numel(), self.lr, self.betas[0], self.betas[1],
-                                    self.eps, _stream()), "b200rnn_adam")
-        return probs, self.loss
+        tf = torch.empty(B, m.text_hidden_dims, device=dev)
+        af = torch.empty(B, m.audio_hidden_dims, device=dev)
+        out = torch.empty(B, self.C, dtype=torch.float32, device=dev)
+        need = int(lib.b200rnn_fuse_head_scratch_floats(B, m.text_hidden_dims, m.audio_hidden_dims,
+                                                        int(self.regression)))
+        if self._dw_part is None or self._dw_part.numel() < need:
+            self._dw_part = torch.empty(need, device=dev)
+        a = self._args(seq, h_n, pooled, tf, af)
+        a.W = self.w.data_ptr()
+        a.w_modal = m.modal_attn.weight.data_ptr() if self.regression else None
+        a.labels = labels.data_ptr()
+        a.out = out.data_ptr()
+        a.loss = self.loss.data_ptr()
+        a.dw_part = self._dw_part.data_ptr()
+        a.dw = self.dw.data_ptr()
+        a.ticket = self.ticket.data_ptr()
+        a.rng_state = self.rng_state.data_ptr()
+        a.rng_consume = (B * max(m.text_hidden_dims, m.audio_hidden_dims) + 3) // 4
+        a.adam_m, a.adam_v, a.adam_step = self.m.data_ptr(), self.v.data_ptr(), self.step_count.data_ptr()
+        a.lr, a.beta1, a.beta2, a.eps = self.lr, self.betas[0], self.betas[1], self.eps
+        a.grad_scale = 1.0 / self.world
+        a.world, a.rank = 1, 0
+        a.do_adam = 1
+        if self.exchange == "peer":
+            a.world, a.rank = self.world, self.rank
+            a.comm_step = self.comm.step.data_ptr()
+            for r in range(self.world):
+                a.comm_buf[r] = self.comm.bufs[r]
+        elif self.exchange == "nccl":
+            a.do_adam = 0
+        with _on(dev):
+            rc = lib.b200rnn_fuse_head(ctypes.byref(a), _stream(dev))
+            _lib.check(rc, "b200rnn_fuse_head")
+            if self.exchange == "nccl":
+                import torch.distributed as dist
+
+                dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
+                _lib.check(lib.b200rnn_adamw(self.w.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(),
+                                             self.v.data_ptr(), self.step_count.data_ptr(), self.grad.numel(), self.lr,
+                                             self.betas[0], self.betas[1], self.eps, 0.0, 1.0 / self.world, 1,
+                                             _stream(dev)), "b200rnn_adamw")
+        return out, self.loss

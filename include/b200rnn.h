@@ -202,6 +202,85 @@ B200RNN_API int b200rnn_adamw(float* p, const float* g, float* m, float* v, floa
                               int advance_step, void* stream);
 
 /*
+ * The whole tail of the fuse step in ONE launch (csrc/fuse_head.cu): attention pooling, the two
+ * Dropout-Linear-ReLU-Dropout heads, the model output (Softmax(fc_final(cat)) of fuse_net_whole.py:368-374, or
+ * ReLU(fc_final(sigmoid(modal_attn x) * x)) of Regression/fuse_net.py:345-351), MyLoss (two-head cross entropy,
+ * fuse_net_whole.py:380-395, or two-head SmoothL1, fuse_net.py:357-366), d loss / d fc_final.0.weight, the
+ * data-parallel sum of that gradient over the ranks (one-shot NVLink exchange through peer-mapped buffers, see
+ * b200rnn_comm_*), and the torch.optim.Adam step (fuse_net_whole.py:416, 456). Replaces b200rnn_attention_pool +
+ * b200rnn_rng_next + 2 x b200rnn_mlp_dropout + b200rnn_fuse_loss_grad + ncclAllReduce + b200rnn_adam.
+ *
+ * All pointers are device pointers. Stages are switched by which pointers are set:
+ *   seq != NULL            : attention pooling from the BiLSTM output (else ctx_in [B,Ht] is the attention context)
+ *   W   != NULL            : output + loss + gradient (+ exchange when world > 1) (+ Adam when do_adam); W == NULL
+ *                            stops after text_feature / audio_feature
+ * Dropout: Philox streams 0,1 (text head in/out) and 2,3 (audio head in/out) keyed by rng_state = {seed, offset}
+ * (read on the device; with the loss stage the offset is advanced by rng_consume at the end, so a captured CUDA graph
+ * draws fresh masks per replay) - the same streams b200rnn_mlp_dropout uses.
+ */
+#define B200RNN_COMM_MAX_WORLD 8
+#define B200RNN_IPC_HANDLE_BYTES 64
+typedef struct b200rnn_fuse_head_args {
+  uint32_t struct_bytes;  /* sizeof(b200rnn_fuse_head_args): binding / library mismatch is rejected            */
+  int32_t B, T, Ht, Ha;   /* batch rows, text time steps, text / audio feature widths (multiples of 4)          */
+  int32_t n_states;       /* rows of h_n summed by the attention query (L*D = 4)                                */
+  int32_t training;       /* 1: Dropout active (model.train())                                                  */
+  float p;                /* Dropout probability of the heads                                                   */
+  int32_t regression;     /* 0: 2-class classification flavour; 1: regression flavour (1 output, float labels)  */
+  int32_t accumulate;     /* dw += gradient instead of dw = gradient                                            */
+  int32_t do_adam;        /* apply the Adam update to W in the same launch                                      */
+  int32_t world, rank;    /* data-parallel ranks (1 = no exchange) and this rank                                */
+  float lr, beta1, beta2, eps, grad_scale; /* Adam hyper-parameters; grad_scale = 1/world                        */
+  uint64_t rng_consume;   /* Philox offset advance per call: ceil(B*max(Ht,Ha)/4)                               */
+  int64_t seq_st, seq_sb; /* element strides of seq: seq[t*seq_st + b*seq_sb + c], c in [0, 2*Ht)              */
+  const float* seq;       /* BiLSTM output [T,B,2*Ht] (fwd | rev halves) or NULL                                */
+  const float* h_n;       /* [n_states,B,Ht]                                                                    */
+  const float* w_att;     /* attention_layer.0.weight [Ht,Ht]                                                   */
+  const float* b_att;     /* attention_layer.0.bias [Ht]                                                        */
+  const float* ctx_in;    /* [B,Ht] attention context when seq == NULL                                          */
+  float* ctx_out;         /* optional [B,Ht]: the attention context before Dropout                              */
+  const float* w_t;       /* fc_out.1.weight [Ht,Ht]                                                            */
+  const float* b_t;       /* fc_out.1.bias [Ht]                                                                 */
+  const float* pooled;    /* [B,Ha] time-summed GRU output                                                      */
+  const float* w_a;       /* fc_audio.1.weight [Ha,Ha]                                                          */
+  const float* b_a;       /* fc_audio.1.bias [Ha]                                                               */
+  uint64_t* rng_state;    /* {seed, offset}; required when training && p > 0                                    */
+  float* text_feature;    /* optional out [B,Ht]                                                                */
+  float* audio_feature;   /* optional out [B,Ha]                                                                */
+  float* W;               /* fc_final.0.weight [C, Ht+Ha], C = 2 (classification) or 1 (regression); NULL = stop */
+  const float* w_modal;   /* regression: modal_attn.weight [F,F] (NULL: output = ReLU(fc_final(x)))              */
+  const void* labels;     /* int64 class indices [B] (classification) or float targets [B] (regression)         */
+  float* out;             /* optional: probs [B,2] or prediction [B]                                            */
+  float* loss;            /* scalar                                                                             */
+  float* dw_part;         /* scratch, b200rnn_fuse_head_scratch_floats() floats                                  */
+  float* dw;              /* [C*(Ht+Ha) + 1]: the reduced gradient (and this rank's loss in the last element)    */
+  uint32_t* ticket;       /* one zero-initialised uint32 (CTA completion counter; the kernel re-arms it)        */
+  float* adam_m;          /* Adam state, each [C*(Ht+Ha)]                                                       */
+  float* adam_v;
+  float* adam_step;       /* device float counting completed steps                                              */
+  uint32_t* comm_step;    /* world > 1: device uint32 step counter of the exchange (zero-initialised)           */
+  void* comm_buf[B200RNN_COMM_MAX_WORLD]; /* world > 1: every rank's exchange buffer as mapped in THIS process    */
+} b200rnn_fuse_head_args;
+
+B200RNN_API size_t b200rnn_fuse_head_scratch_floats(int B, int Ht, int Ha, int regression);
+B200RNN_API int b200rnn_fuse_head(const b200rnn_fuse_head_args* args, void* stream);
+
+/*
+ * Exchange buffers of the one-shot gradient exchange (setup path; the only allocation the library ever makes, done
+ * once per process, never on the hot path). Each rank creates its buffer, ships the 64-byte CUDA IPC handle to its
+ * peers (any side channel, e.g. torch.distributed.all_gather), and opens theirs:
+ *   b200rnn_comm_bytes()               size of a buffer (flags + 2 parities x MAX_WORLD slots of 4 KB)
+ *   b200rnn_comm_create(&buf, handle)  cudaMalloc + zero + cudaIpcGetMemHandle on the current device
+ *   b200rnn_comm_open(handle, &peer)   cudaIpcOpenMemHandle (peer access over NVLink is enabled lazily)
+ *   b200rnn_comm_close / _destroy      unmap a peer buffer / free the own one
+ */
+B200RNN_API size_t b200rnn_comm_bytes(void);
+B200RNN_API int b200rnn_comm_create(void** local_buf, unsigned char* ipc_handle_out);
+B200RNN_API int b200rnn_comm_open(const unsigned char* ipc_handle, void** peer_buf);
+B200RNN_API int b200rnn_comm_close(void* peer_buf);
+B200RNN_API int b200rnn_comm_destroy(void* local_buf);
+
+/*
  * Optional device-side timing of the library's own launches (CUDA event pairs on the launching stream),
  * used by bench.py for the roofline figure. kind: 0 = forward recurrence, 1 = backward recurrence,
  * 2 = GEMM, 3 = other. Do not enable while capturing a CUDA graph.

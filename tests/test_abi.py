@@ -102,3 +102,16 @@ def test_ctypes_argtypes_match_the_header_prototypes_parameter_by_parameter():
         # aliases them (c_size_t is c_ulong is c_uint64 on this platform)
         norm = lambda ks: ["u64" if k == "size" else k for k in ks]  # noqa: E731
         assert norm(got) == norm(want), f"{name}: binding {got} vs header {want}"
+
+
+def test_fuse_head_argument_block_matches_the_library():
+    """The ctypes mirror of b200rnn_fuse_head_args must have the library's size; a stale binding is rejected with a
+    message instead of corrupting the launch (checked before anything touches the device)."""
+    lib = _lib.load()
+    a = _lib.FuseHeadArgs(B=0, Ht=128, Ha=256)
+    assert lib.b200rnn_fuse_head(ctypes.byref(a), None) == 0      # B == 0: accepted, nothing launched
+    a.struct_bytes -= 8
+    assert lib.b200rnn_fuse_head(ctypes.byref(a), None) == -1
+    assert b"mismatched argument block" in lib.b200rnn_last_error()
+    assert lib.b200rnn_comm_bytes() >= 2 * 8 * 768 * 4
+    assert lib.b200rnn_fuse_head_scratch_floats(128, 128, 256, 0) == 128 * (2 * 384 + 1)

@@ -188,3 +188,86 @@ def test_flat_adamw_matches_torch_adamw_with_reference_grouping():
     # the parameters really live in the flat buffers now
     g0 = opt2.groups[0]
     assert all(p.data_ptr() >= g0.flat_p.data_ptr() for p in g0.params)
+
+
+def test_fuse_head_train_mode_equals_the_unfused_kernel_chain_with_the_same_rng():
+    """Train mode (dropout 0.3): the single-launch head draws the same Philox streams as attention_pool +
+    mlp_dropout(stream 0) + mlp_dropout(stream 2) run one after the other on the same {seed, offset}, so the features
+    must agree to rounding although dropout is on."""
+    import b200rnn
+    from b200rnn import fused_head
+    from b200rnn.functional import rnn_forward_fused
+
+    m = _fuse_model(train=True)
+    m.lstm_net.eval()            # keep the encoders deterministic: only the head dropout is under test here
+    m.lstm_net_audio.eval()
+    step = b200rnn.FusedFuseStep(m)
+    torch.manual_seed(8)
+    batch = b200rnn.FuseBatch(torch.randn(33, 12, 256, device=DEV), torch.randn(33, 7, 1024, device=DEV))
+    state0 = step.rng_state.clone()
+    tf, af = step.features(batch)
+    hdr = step.rng_hdr.clone()
+    assert hdr[0].item() == state0[0].item() and hdr[1].item() == state0[1].item()
+    assert step.rng_state[1].item() > state0[1].item(), "the device-side RNG offset must advance"
+    with torch.no_grad():
+        seq, h_n, _ = rnn_forward_fused(batch.text.permute(1, 0, 2), m.lstm_net._flat_weights, m.lstm_net._config(),
+                                        m.lstm_net._rng_state)
+        ctx = fused_head.attention_pool(seq, h_n, m.attention_layer)
+        tf_ref = fused_head.mlp_dropout(ctx, m.fc_out[1], 0.3, True, hdr, 0)
+        pooled = m.lstm_net_audio.forward_ln_sum(batch.audio, m.ln)
+        af_ref = fused_head.mlp_dropout(pooled, m.fc_audio[1], 0.3, True, hdr, 2)
+    torch.cuda.synchronize()
+    assert (tf == 0).float().mean().item() > 0.2, "output dropout must zero ~30 % (plus ReLU zeros)"
+    assert ((tf == 0) == (tf_ref == 0)).all() and ((af == 0) == (af_ref == 0)).all(), "same masks"
+    assert (tf - tf_ref).abs().max().item() < 1e-5
+    assert (af - af_ref).abs().max().item() < 2e-4   # |pooled| ~ 120 * |h|: rounding of a differently ordered dot
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_fused_fuse_step_regression_flavour_matches_cpu_oracle(train):
+    """Regression/fuse_net.py:345-366, 373-412: sigmoid(modal_attn) gate + ReLU output, two-head SmoothL1 MyLoss, Adam on
+    fc_final.0.weight - three steps against oracle.ref_models.RefFusion(regression=True) on CPU (dropout 0 in train)."""
+    import b200rnn
+    from oracle import ref_models
+
+    args = dict(text_embed_size=1024, text_hidden_dims=128, rnn_layers=2, dropout=0.0 if train else 0.3, num_classes=1,
+                audio_hidden_dims=256, audio_embed_size=256)
+    torch.manual_seed(0)
+    ref = ref_models.RefFusion(regression=True, **args)
+    mine = b200rnn.fusion_net(regression=True, **args)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(DEV)
+    ref.train(train)
+    mine.train(train)
+    lr = 1e-3
+    opt = torch.optim.Adam([ref.fc_final[0].weight], lr=lr)
+    step = b200rnn.FusedFuseStep(mine, lr=lr)
+    g = torch.Generator().manual_seed(17)
+    for _ in range(3):
+        audio, text = torch.randn(20, 15, 256, generator=g), torch.randn(20, 5, 1024, generator=g)
+        y = torch.rand(20, generator=g) * 3.0          # PHQ-like targets around the SmoothL1 knee
+        opt.zero_grad()
+        tf_r, af_r = ref.pretrained_feature_tensors(audio, text)
+        out_r = ref(torch.cat((tf_r, af_r), dim=1))
+        loss_r = ref_models.ref_fusion_loss(tf_r, af_r, y.view(-1, 1), ref)
+        loss_r.backward()
+        opt.step()
+        out_m, loss_m = step(b200rnn.FuseBatch(audio.to(DEV), text.to(DEV)), y.to(DEV))
+        torch.cuda.synchronize()
+        assert (out_m.cpu() - out_r.detach()).abs().max().item() < 1e-4
+        assert abs(loss_m.item() - loss_r.item()) < 1e-5 * max(1.0, abs(loss_r.item()))
+        assert (mine.fc_final[0].weight.detach().cpu() - ref.fc_final[0].weight.detach()).abs().max().item() < 2e-6
+
+
+def test_fused_fuse_step_rejects_bad_labels():
+    import b200rnn
+
+    m = _fuse_model(train=False)
+    step = b200rnn.FusedFuseStep(m)
+    batch = b200rnn.FuseBatch(torch.randn(4, 6, 256, device=DEV), torch.randn(4, 3, 1024, device=DEV))
+    with pytest.raises(ValueError):
+        step(batch, torch.zeros(3, dtype=torch.int64, device=DEV))
+    _, loss = step(batch, torch.tensor([0, 1, 1, 0], dtype=torch.int32, device=DEV))   # int32 is converted, not misread
+    assert torch.isfinite(loss)
+    _, loss = step(batch, torch.tensor([0, 1, 2, 0], device=DEV))                      # class 2 does not exist
+    assert torch.isnan(loss)

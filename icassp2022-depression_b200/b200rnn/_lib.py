@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("B200RNN_LIB") or os.path.join(os.path.dirname(_HERE),
 GRU, LSTM = 0, 1
 FLAG_ACCUMULATE_GRADS = 1
 FLAG_SAVE_FOR_BACKWARD = 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/b200rnn.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
@@ -28,6 +28,8 @@ SYMBOLS = (
     "b200rnn_forward",
     "b200rnn_forward_fused",
     "b200rnn_backward",
+    "b200rnn_wcache_bytes",
+    "b200rnn_prepare_weights",
     "b200rnn_gemm_f32",
     "b200rnn_attention_pool",
     "b200rnn_mlp_dropout",
@@ -143,7 +145,11 @@ def load() -> ctypes.CDLL:
     ]
     lib.b200rnn_forward_fused.restype = c_int
     lib.b200rnn_forward_fused.argtypes = lib.b200rnn_forward.argtypes[:-1] + [c_void_p, c_void_p, c_float, c_void_p,
-                                                                              c_void_p, c_void_p]
+                                                                              c_void_p, c_void_p, c_void_p]
+    lib.b200rnn_wcache_bytes.restype = c_int
+    lib.b200rnn_wcache_bytes.argtypes = [POINTER(Desc), POINTER(c_size_t)]
+    lib.b200rnn_prepare_weights.restype = c_int
+    lib.b200rnn_prepare_weights.argtypes = [POINTER(Desc), POINTER(c_void_p), c_void_p, c_void_p]
     lib.b200rnn_backward.restype = c_int
     lib.b200rnn_backward.argtypes = [
         POINTER(Desc), c_void_p, c_int64, c_int64,   # desc, x, strides

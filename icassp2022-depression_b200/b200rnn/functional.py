@@ -99,7 +99,7 @@ class _RNNFunction(torch.autograd.Function):
                     y.data_ptr(), ys_t, ys_b, h_n.data_ptr(), c_n.data_ptr() if c_n is not None else None,
                     reserve.data_ptr() if save else None, scratch.data_ptr(),
                     0, 0, rng_state.data_ptr() if rng_state is not None else None, None, None, 0.0, None,
-                    lengths.data_ptr() if lengths is not None else None, _stream_ptr(dev))
+                    lengths.data_ptr() if lengths is not None else None, None, _stream_ptr(dev))
             _lib.check(rc, "b200rnn_forward")
         else:
             h_n.zero_()
@@ -219,7 +219,8 @@ def rnn_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNNConfig
 @torch.no_grad()
 def rnn_forward_fused(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNNConfig,
                       rng_state: Optional[torch.Tensor] = None, ln_weight: Optional[torch.Tensor] = None,
-                      ln_bias: Optional[torch.Tensor] = None, ln_eps: float = 1e-5, pool_sum: bool = False):
+                      ln_bias: Optional[torch.Tensor] = None, ln_eps: float = 1e-5, pool_sum: bool = False,
+                      wcache: Optional[torch.Tensor] = None):
     """No-grad forward with the shell fusions of ``b200rnn_forward_fused``: optional LayerNorm prologue on ``x``
     and, with ``pool_sum``, the sum over time of the output instead of the sequence (``[B, D*H]``).
 
@@ -253,9 +254,27 @@ def rnn_forward_fused(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNN
             rng_state.data_ptr() if rng_state is not None else None,
             ln_weight.data_ptr() if ln_weight is not None else None,
             ln_bias.data_ptr() if ln_bias is not None else None,
-            float(ln_eps), pool_ptr, None, _stream_ptr(dev))
+            float(ln_eps), pool_ptr, None, wcache.data_ptr() if wcache is not None else None, _stream_ptr(dev))
     _lib.check(rc, "b200rnn_forward_fused")
     return (out, h_n) if c_n is None else (out, h_n, c_n)
+
+
+def prepare_weights(weights: Sequence[torch.Tensor], cfg: RNNConfig) -> torch.Tensor:
+    """TF32 hi/lo split of every ``weight_ih`` (``b200rnn_prepare_weights``): the weight cache ``rnn_forward_fused``
+    accepts so that frozen encoders split their weights once instead of once per step."""
+    lib = _lib.load()
+    dev = weights[0].device
+    for i, w in enumerate(weights):
+        _require_cuda_f32(w, f"weight[{i}]")
+    desc = _make_desc(cfg, 1, 1, False)
+    n = ctypes.c_size_t(0)
+    _lib.check(lib.b200rnn_wcache_bytes(ctypes.byref(desc), ctypes.byref(n)), "b200rnn_wcache_bytes")
+    cache = torch.empty(int(n.value), dtype=torch.uint8, device=dev)
+    params = _lib.ptr_array([w.data_ptr() for w in weights])
+    with _on(dev):
+        rc = lib.b200rnn_prepare_weights(ctypes.byref(desc), params, cache.data_ptr(), _stream_ptr(dev))
+    _lib.check(rc, "b200rnn_prepare_weights")
+    return cache
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kcontig: bool = True, b_kcontig: bool = True,

@@ -144,7 +144,7 @@ class FusedFuseStep:
     def _encoders(self, batch: FuseBatch):
         m = self.model
         seq, h_n, _ = rnn_forward_fused(batch.text.permute(1, 0, 2), m.lstm_net._flat_weights, m.lstm_net._config(),
-                                        m.lstm_net._rng_state)
+                                        m.lstm_net._rng_state, wcache=m.lstm_net.frozen_weight_cache())
         pooled = m.lstm_net_audio.forward_ln_sum(batch.audio, None if self.regression else m.ln)
         return seq, h_n.contiguous(), pooled
 

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import RNNConfig, rnn_forward, rnn_forward_fused
+from .functional import RNNConfig, prepare_weights, rnn_forward, rnn_forward_fused
 
 _TORCH_GRU = nn.GRU
 _TORCH_LSTM = nn.LSTM
@@ -84,6 +84,7 @@ class _B200RNNBase(nn.Module):
                              persistent=False)
         # optional hook: callable(weights) -> list of gradient target tensors (see b200rnn.dp.GradBucket)
         self._grad_sink: Optional[Callable] = None
+        self._wcache = None        # (key, tensor): TF32 split of the weight_ih matrices while they are frozen
         self.reset_parameters()
 
     # -- torch.nn.RNNBase API surface ---------------------------------------------------------------
@@ -120,11 +121,31 @@ class _B200RNNBase(nn.Module):
         super().__setstate__(d)
         if "_grad_sink" not in self.__dict__:
             self._grad_sink = None
+        self._wcache = None
 
     def __getstate__(self):
         d = self.__dict__.copy()
         d["_grad_sink"] = None  # closures over buckets are not picklable / not part of the model
+        d["_wcache"] = None     # derived data
         return d
+
+    def frozen_weight_cache(self):
+        """TF32-split ``weight_ih`` cache for the no-grad fused forward, or None.
+
+        Only while EVERY weight of the module is frozen (``requires_grad=False``, the fuse scripts' encoders:
+        fuse_net_whole.py:590-593) - nothing this library launches updates such a tensor behind PyTorch's back. The
+        cache is keyed on the parameters' storage addresses and version counters, so ``load_state_dict``, ``.to()`` or
+        an in-place edit refresh it; trainable modules never use it (their weights change every step anyway)."""
+        ws = self._flat_weights
+        if any(w.requires_grad for w in ws) or not ws[0].is_cuda:
+            self._wcache = None
+            return None
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        if self._wcache is None or self._wcache[0] != key:
+            if torch.cuda.is_current_stream_capturing():
+                return None   # never (re)build under capture: a replay would not redo it
+            self._wcache = (key, prepare_weights(ws, self._config()))
+        return self._wcache[1]
 
     def _config(self) -> RNNConfig:
         return RNNConfig(mode=self._mode, input_size=self.input_size, hidden_size=self.hidden_size,
@@ -173,7 +194,8 @@ class _B200RNNBase(nn.Module):
         if fusable:
             out = rnn_forward_fused(input, self._flat_weights, self._config(), self._rng_state,
                                     ln.weight if ln is not None else None, ln.bias if ln is not None else None,
-                                    ln.eps if ln is not None else 1e-5, pool_sum=True)
+                                    ln.eps if ln is not None else 1e-5, pool_sum=True,
+                                    wcache=self.frozen_weight_cache())
             return out[0]
         seq = self(ln(input) if ln is not None else input)[0]
         return seq.sum(dim=1 if self.batch_first else 0)

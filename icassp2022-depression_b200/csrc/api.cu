@@ -187,6 +187,26 @@ void make_scratch(const Dims& d, ScratchLayout* s) {
   s->b_total = off;
 }
 
+// ---- weight cache layout (floats): per (layer, direction) the TF32 hi then lo split of weight_ih [G*H, I_l] -------
+struct WCacheLayout {
+  size_t hi[8][2], lo[8][2];
+  size_t total;
+};
+
+void make_wcache(const Dims& d, WCacheLayout* w) {
+  size_t off = 0;
+  for (int l = 0; l < d.L && l < 8; ++l) {
+    const size_t Il = l == 0 ? (size_t)d.I : d.DH;
+    for (int k = 0; k < d.D; ++k) {
+      w->hi[l][k] = off;
+      off += align_up(d.GH * Il, ALIGN_F);
+      w->lo[l][k] = off;
+      off += align_up(d.GH * Il, ALIGN_F);
+    }
+  }
+  w->total = off;
+}
+
 inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 }  // namespace
@@ -233,12 +253,19 @@ B200RNN_API int b200rnn_forward_fused(const b200rnn_desc* desc, const float* x, 
                                       const float* const* params, float* y, int64_t ys_t, int64_t ys_b, float* h_n,
                                       float* c_n, void* reserve, void* scratch, uint64_t seed, uint64_t offset,
                                       uint64_t* rng_state, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                                      float* y_pool, const int32_t* lengths, void* stream_) {
+                                      float* y_pool, const int32_t* lengths, const void* wcache, void* stream_) {
   Dims d;
   int rc = check_desc(desc, &d);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   if (d.B == 0 || d.T == 0) return B200RNN_OK;
+  if (wcache && !aligned_to(wcache, 256)) {
+    set_error("forward: the weight cache must be 256-byte aligned");
+    return B200RNN_ERR_INVALID;
+  }
+  WCacheLayout wl;
+  make_wcache(d, &wl);
+  const float* WC = static_cast<const float*>(wcache);
   const bool save = (desc->flags & B200RNN_FLAG_SAVE_FOR_BACKWARD) != 0;
   if (!x || !params || (!y && !y_pool) || !h_n || (d.mode == B200RNN_LSTM && !c_n)) {
     set_error("forward: null pointer argument");
@@ -340,6 +367,10 @@ B200RNN_API int b200rnn_forward_fused(const b200rnn_desc* desc, const float* x, 
         g.tc_ws = tc_ws;
         g.tc_ws_bytes = sl.f_tc_bytes;
         g.tc_a_presplit = 1;
+        if (WC) {  // weight_ih was split once by b200rnn_prepare_weights (frozen encoders)
+          g.tc_b_hi = WC + wl.hi[l][k];
+          g.tc_b_lo = WC + wl.lo[l][k];
+        }
       }
       rc = launch_gemm(g, nullptr, 0, st);
       if (rc) return rc;
@@ -383,7 +414,50 @@ B200RNN_API int b200rnn_forward(const b200rnn_desc* desc, const float* x, int64_
                                 float* c_n, void* reserve, void* scratch, uint64_t seed, uint64_t offset,
                                 uint64_t* rng_state, void* stream_) {
   return b200rnn_forward_fused(desc, x, xs_t, xs_b, params, y, ys_t, ys_b, h_n, c_n, reserve, scratch, seed, offset,
-                               rng_state, nullptr, nullptr, 0.f, nullptr, nullptr, stream_);
+                               rng_state, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, stream_);
+}
+
+B200RNN_API int b200rnn_wcache_bytes(const b200rnn_desc* desc, size_t* bytes) {
+  Dims d;
+  int rc = check_desc(desc, &d);
+  if (rc) return rc;
+  if (d.L > 8) {
+    set_error("num_layers %d > 8 unsupported", d.L);
+    return B200RNN_ERR_UNSUPPORTED;
+  }
+  WCacheLayout wl;
+  make_wcache(d, &wl);
+  if (bytes) *bytes = (wl.total + ALIGN_F) * sizeof(float);
+  return B200RNN_OK;
+}
+
+B200RNN_API int b200rnn_prepare_weights(const b200rnn_desc* desc, const float* const* params, void* wcache,
+                                        void* stream_) {
+  Dims d;
+  int rc = check_desc(desc, &d);
+  if (rc) return rc;
+  if (!params || !wcache || !aligned_to(wcache, 256) || d.L > 8) {
+    set_error("prepare_weights: null / misaligned argument");
+    return B200RNN_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  WCacheLayout wl;
+  make_wcache(d, &wl);
+  float* WC = static_cast<float*>(wcache);
+  for (int l = 0; l < d.L; ++l) {
+    const int Il = l == 0 ? d.I : (int)d.DH;
+    for (int k = 0; k < d.D; ++k) {
+      const float* w_ih = params[(size_t)(l * d.D + k) * 4];
+      if (!w_ih) {
+        set_error("prepare_weights: null weight_ih (layer %d dir %d)", l, k);
+        return B200RNN_ERR_INVALID;
+      }
+      if (Il % 4 != 0) continue;  // such a layer takes the FFMA projection, which reads the fp32 weights directly
+      rc = tc_split(w_ih, simple_rows(Il), (int)d.GH, Il, WC + wl.hi[l][k], WC + wl.lo[l][k], st);
+      if (rc) return rc;
+    }
+  }
+  return B200RNN_OK;
 }
 
 B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64_t xs_t, int64_t xs_b,

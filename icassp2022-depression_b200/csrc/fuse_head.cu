@@ -31,7 +31,8 @@ namespace b200rnn {
 namespace {
 
 constexpr int HEAD_THREADS = 256;
-constexpr int HEAD_ROWS = 2;        // batch rows per CTA: each weight row fetched from L2 serves two rows
+constexpr int HEAD_ROWS = 1;        // batch rows per CTA: B CTAs, the chip is covered at B = 128 (latency-bound work)
+constexpr int ROWSTAT = 8;          // floats per batch row handed to the last CTA: dt[2], da[2], row loss (padded)
 constexpr int COMM_MAX_WORLD = B200RNN_COMM_MAX_WORLD;
 constexpr int COMM_PAYLOAD = 1024;  // floats per slot (fc_final.0.weight is 2 x 384 = 768; + loss)
 constexpr size_t COMM_FLAG_OFF = 0;                 // uint32 flags[2][MAX_WORLD]
@@ -73,7 +74,7 @@ template <int R, bool RELU>
 __device__ __forceinline__ void matvec_rows(const float* __restrict__ W, const float* __restrict__ bias,
                                             const float* xs, int ldx, float* ys, int ldy, int n_out, int n, int warp,
                                             int nwarps, int lane) {
-  constexpr int UNR = 4;
+  constexpr int UNR = 8;
   for (int i0 = warp * UNR; i0 < n_out; i0 += nwarps * UNR) {
     float acc[UNR][R];
 #pragma unroll
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_f
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = HEAD_THREADS / 32;
   const int b0 = blockIdx.x * R;
 
+  float* feat_ws = a.dw_part ? a.dw_part + (size_t)B * ROWSTAT : nullptr;  // [B][F] features for the gradient pass
   const bool drop = a.training && a.p > 0.f;
   const uint32_t thr = (uint32_t)fminf(a.p * 4294967296.0f, 4294967295.0f);
   const float scale = a.p < 1.f ? 1.f / (1.f - a.p) : 0.f;
@@ -291,15 +293,16 @@ __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_f
           if (lane == 0) a.out[b] = a.w_modal ? fmaxf(po, 0.f) : fmaxf(pt[0] + pa[0], 0.f);
         }
       }
-      float* part = a.dw_part + (size_t)b * (C * F + 1);
-      for (int j = lane; j < F; j += 32) {
-        const float v = f[j];
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-          if (c < C) part[c * F + j] = ((j < Ht) ? dt[c] : da[c]) * v;
+      if (lane == 0) {  // what the last CTA needs from this row: the four logit gradients and the row's loss
+        float* st = a.dw_part + (size_t)b * ROWSTAT;
+        st[0] = dt[0]; st[1] = dt[1]; st[2] = da[0]; st[3] = da[1]; st[4] = lrow * invB;
       }
-      if (lane == 0) part[C * F] = lrow * invB;
     }
+  }
+  // the features of this CTA's rows, for the gradient pass of the last CTA (dW = d^T [tf | af])
+  for (int idx = tid; idx < R * F; idx += HEAD_THREADS) {
+    const int r = idx / F, j = idx - r * F, b = b0 + r;
+    if (b < B) feat_ws[(size_t)b * F + j] = feat[idx];
   }
 
   // ---------------- last CTA: deterministic reduction over the batch, peer exchange, Adam --------------------------
@@ -309,11 +312,39 @@ __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_f
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const int NP = C * F + 1;  // gradient + loss
-  for (int i = tid; i < NP; i += HEAD_THREADS) {
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += __ldcg(a.dw_part + (size_t)b * NP + i);  // fixed order => deterministic
-    a.dw[i] = a.accumulate ? a.dw[i] + s : s;
+  // dW[c][j] = sum_b d[b][c] * f[b][j]: a [C x B] x [B x F] product. Thread j walks the batch in a fixed order
+  // (deterministic), every load is a coalesced row segment of the feature matrix; the 5 per-row scalars sit in shared
+  // memory (the feature staging area of this CTA is free now).
+  float* rst = sm;  // [B][ROWSTAT] : B * 8 floats <= the R*(3Ht+2F+Ha+T) floats carved above? checked on the host
+  for (int idx = tid; idx < B * ROWSTAT; idx += HEAD_THREADS) rst[idx] = __ldcg(a.dw_part + idx);
+  __syncthreads();
+  for (int j = tid; j < F; j += HEAD_THREADS) {
+    float g0 = 0.f, g1 = 0.f;
+    const int so = (j < Ht) ? 0 : 2;
+    int b = 0;
+    for (; b + 8 <= B; b += 8) {
+      float fv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) fv[u] = __ldcg(feat_ws + (size_t)(b + u) * F + j);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        g0 = fmaf(rst[(b + u) * ROWSTAT + so], fv[u], g0);
+        g1 = fmaf(rst[(b + u) * ROWSTAT + so + 1], fv[u], g1);
+      }
+    }
+    for (; b < B; ++b) {
+      const float fv = __ldcg(feat_ws + (size_t)b * F + j);
+      g0 = fmaf(rst[b * ROWSTAT + so], fv, g0);
+      g1 = fmaf(rst[b * ROWSTAT + so + 1], fv, g1);
+    }
+    a.dw[j] = a.accumulate ? a.dw[j] + g0 : g0;
+    if (C == 2) a.dw[F + j] = a.accumulate ? a.dw[F + j] + g1 : g1;
+  }
+  if (warp == 0) {  // loss = sum of the row losses, fixed order
+    float l = 0.f;
+    for (int b = lane; b < B; b += 32) l += rst[b * ROWSTAT + 4];
+    l = warp_sum(l);
+    if (lane == 0) a.dw[C * F] = l;
   }
   __syncthreads();
   if (a.world > 1) {
@@ -373,9 +404,11 @@ __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_f
   }
 }
 
-size_t head_smem_floats(int Ht, int Ha, int T) {
+size_t head_smem_floats(int B, int Ht, int Ha, int T, bool loss_stage) {
   const int F = Ht + Ha, Tpad = (T + 3) & ~3;
-  return (size_t)HEAD_ROWS * (3 * Ht + 2 * F + Ha + Tpad) + 32;
+  size_t n = (size_t)HEAD_ROWS * (3 * Ht + 2 * F + Ha + Tpad) + 32;
+  const size_t rst = loss_stage ? (size_t)B * ROWSTAT : 0;  // the last CTA re-uses the area for the per-row scalars
+  return n > rst ? n : rst;
 }
 
 }  // namespace
@@ -386,8 +419,8 @@ using namespace b200rnn;
 extern "C" {
 
 B200RNN_API size_t b200rnn_fuse_head_scratch_floats(int B, int Ht, int Ha, int regression) {
-  const int C = regression ? 1 : 2;
-  return (size_t)(B > 0 ? B : 0) * (size_t)(C * (Ht + Ha) + 1);
+  (void)regression;
+  return (size_t)(B > 0 ? B : 0) * (size_t)(ROWSTAT + Ht + Ha);  // per-row scalars, then the feature matrix [B, F]
 }
 
 B200RNN_API int b200rnn_fuse_head(const b200rnn_fuse_head_args* args, void* stream_) {
@@ -434,7 +467,7 @@ B200RNN_API int b200rnn_fuse_head(const b200rnn_fuse_head_args* args, void* stre
         }
     }
   }
-  const size_t smem = head_smem_floats(a.Ht, a.Ha, a.seq ? a.T : 0) * sizeof(float);
+  const size_t smem = head_smem_floats(a.B, a.Ht, a.Ha, a.seq ? a.T : 0, a.W != nullptr) * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("fuse_head: widths too large for one CTA");
     return B200RNN_ERR_UNSUPPORTED;

@@ -23,6 +23,10 @@ struct GemmParams {
   void* tc_ws;
   size_t tc_ws_bytes;
   int tc_a_presplit;  // the A operand's hi/lo halves already sit at tc_ws (see tc_a_hi / tc_a_lo)
+  // optional: the B operand (a weight matrix) already split into dense [N,K] hi / lo matrices by an earlier call
+  // (b200rnn_prepare_weights: frozen encoders split their W_ih once, not once per step)
+  const float* tc_b_hi;
+  const float* tc_b_lo;
 };
 
 // where launch_gemm_tc expects / puts the split A operand inside its workspace

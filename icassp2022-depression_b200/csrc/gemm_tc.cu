@@ -586,13 +586,19 @@ int launch_gemm_tc(const GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t 
   }
   float* a_hi = tc_a_hi(ws);
   float* a_lo = tc_a_lo(ws, p.M, p.K);
-  float* b_hi = a_lo + (size_t)p.M * p.K;
-  float* b_lo = b_hi + (size_t)p.N * p.K;
+  const float* b_hi = p.tc_b_hi;
+  const float* b_lo = p.tc_b_lo;
   int rc = B200RNN_OK;
   if (!p.tc_a_presplit) rc = tc_split(p.A, p.a_rows, p.M, p.K, a_hi, a_lo, stream);
   if (rc) return rc;
-  rc = tc_split(p.B, p.b_rows, p.N, p.K, b_hi, b_lo, stream);
-  if (rc) return rc;
+  if (!b_hi || !b_lo) {
+    float* w_hi = a_lo + (size_t)p.M * p.K;
+    float* w_lo = w_hi + (size_t)p.N * p.K;
+    rc = tc_split(p.B, p.b_rows, p.N, p.K, w_hi, w_lo, stream);
+    if (rc) return rc;
+    b_hi = w_hi;
+    b_lo = w_lo;
+  }
   TcOperand A{a_hi, a_lo, p.K}, B{b_hi, b_lo, p.K};
   return tc_gemm_presplit(A, B, p.M, p.N, p.K, p.C, p.c_rows, p.bias1, p.bias2, p.bias2_n, 0, nullptr, 0, stream);
 }

@@ -114,4 +114,4 @@ def test_fuse_head_argument_block_matches_the_library():
     assert lib.b200rnn_fuse_head(ctypes.byref(a), None) == -1
     assert b"mismatched argument block" in lib.b200rnn_last_error()
     assert lib.b200rnn_comm_bytes() >= 2 * 8 * 768 * 4
-    assert lib.b200rnn_fuse_head_scratch_floats(128, 128, 256, 0) == 128 * (2 * 384 + 1)
+    assert lib.b200rnn_fuse_head_scratch_floats(128, 128, 256, 0) == 128 * (8 + 384)

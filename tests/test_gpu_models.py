@@ -185,3 +185,31 @@ def test_fused_path_falls_back_under_autograd():
     out = gru.forward_ln_sum(x, ln)
     out.sum().backward()
     assert x.grad is not None and torch.isfinite(x.grad).all()
+
+
+def test_frozen_weight_cache_is_bitwise_neutral_and_follows_weight_updates():
+    """b200rnn_prepare_weights: frozen encoders split weight_ih once; the cached path must be bit-identical to the
+    split-on-the-fly path, must refresh after an in-place weight edit, and must be off for trainable modules."""
+    import b200rnn
+
+    torch.manual_seed(3)
+    gru = b200rnn.GRU(256, 256, num_layers=2, batch_first=True).to(DEV).eval()
+    ln = torch.nn.LayerNorm(256).to(DEV)
+    x = torch.randn(9, 14, 256, device=DEV)
+    with torch.no_grad():
+        assert gru.frozen_weight_cache() is None            # trainable: no cache
+        base = gru.forward_ln_sum(x, ln).clone()
+        for p in gru.parameters():
+            p.requires_grad = False
+        cache = gru.frozen_weight_cache()
+        assert cache is not None and gru.frozen_weight_cache() is cache     # built once
+        assert torch.equal(gru.forward_ln_sum(x, ln), base)
+        gru.weight_ih_l1.mul_(1.5)                          # in-place edit bumps the version counter
+        cache2 = gru.frozen_weight_cache()
+        assert cache2 is not cache
+        got = gru.forward_ln_sum(x, ln).clone()
+        for p in gru.parameters():
+            p.requires_grad = True
+        assert gru.frozen_weight_cache() is None
+        assert torch.equal(gru.forward_ln_sum(x, ln), got)  # uncached result with the edited weights
+        assert not torch.equal(got, base)

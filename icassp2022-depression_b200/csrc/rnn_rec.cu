@@ -62,10 +62,14 @@ struct RecCfg {
 };
 
 // All-gather `val` (owned by lane (unit, batch) of every warp) into vec[b][col0 + unit] of all C CTAs:
-// 4 shuffles gather 4 consecutive units, one st.async.v4 per (destination, chunk).
-template <int C, int KL, int UPL, int BS>
+// 4 shuffles gather 4 consecutive units, one 16-byte store per (destination, chunk).
+// Remote destinations get st.async (data + complete_tx on the destination's per-source mbarrier). With LOCAL_SELF the
+// CTA's own copy does not take the trip through the cluster network (measured: >= 600 cycles from the store to the
+// barrier flip even for the own CTA, tools/trace_rec.py): it is written with ordinary st.shared and published with one
+// mbarrier.arrive per warp on the own-source barrier (initialised with the warp count instead of a byte count).
+template <int C, int KL, int UPL, int BS, bool LOCAL_SELF = false>
 __device__ __forceinline__ void allgather_units(float val, float* vec_local, int vstride, int col0,
-                                                uint64_t* bar_local, int lane) {
+                                                uint64_t* bar_local, int lane, uint32_t rank = 0) {
   using LM = LaneMap<KL, UPL, BS>;
   constexpr int UPW = LM::UPW;
   constexpr int NCH = UPW * BS / 4;  // 16-byte chunks per destination
@@ -84,9 +88,18 @@ __device__ __forceinline__ void allgather_units(float val, float* vec_local, int
     v.z = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 2, b));
     v.w = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 3, b));
     if (act) {
-      const uint32_t dst = ptx::smem_u32(&vec_local[b * vstride + col0 + quad * 4]);
-      ptx::st_async_v4(ptx::mapa(dst, (uint32_t)r), v, ptx::mapa(bar_addr, (uint32_t)r));
+      float* dst_ptr = &vec_local[b * vstride + col0 + quad * 4];
+      if (LOCAL_SELF && (uint32_t)r == rank) {
+        *reinterpret_cast<float4*>(dst_ptr) = v;
+      } else {
+        const uint32_t dst = ptx::smem_u32(dst_ptr);
+        ptx::st_async_v4(ptx::mapa(dst, (uint32_t)r), v, ptx::mapa(bar_addr, (uint32_t)r));
+      }
     }
+  }
+  if (LOCAL_SELF) {
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(bar_local);
   }
 }
 
@@ -117,7 +130,10 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
   const float* w_hh = p.w_hh[dir];
 
   if (tid == 0) {
-    for (int i = 0; i < Cfg::NBAR; ++i) ptx::mbar_init(&bars[i], 1);
+    // [0]: weights (tx bytes). [1 + buf*C + src]: slice of source CTA `src` - remote sources complete tx bytes
+    // (one arrive.expect_tx by thread 0 per phase), the CTA's OWN slice is published by one plain arrive per warp
+    for (int i = 0; i < Cfg::NBAR; ++i)
+      ptx::mbar_init(&bars[i], (i >= 1 && (uint32_t)((i - 1) % C) == rank) ? (uint32_t)Cfg::NW : 1u);
     ptx::fence_mbar_init();
   }
   __syncthreads();
@@ -161,6 +177,23 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     for (int g = 0; g < G; ++g) gi[g] = gp[g * H];
   }
 
+  // Global stores of a step (output, saved gates) are DEFERRED into the next step, behind its first chunk: they used to
+  // sit between the exchange and the next contraction, i.e. on the serial path of every step (225 cycles).
+  float pend_y = 0.f, pend_s0 = 0.f, pend_s1 = 0.f, pend_s2 = 0.f, pend_s3 = 0.f, pend_sx = 0.f;
+  auto flush_pending = [&](int tp) {
+    if (valid) {
+      if (p.y) p.y[(long long)tp * p.y_st + (long long)b * p.y_sb + dir * H + j] = pend_y;
+      if (p.training) {
+        float* gp = gates + ((size_t)tp * B + b) * GH + j;
+        gp[0] = pend_s0;
+        gp[H] = pend_s1;
+        gp[2 * H] = pend_s2;
+        if (G == 4) gp[3 * H] = pend_s3;
+        extra[((size_t)tp * B + b) * H + j] = pend_sx;
+      }
+    }
+  };
+
   for (int step = 0; step < T; ++step) {
     const int t = dir ? (T - 1 - step) : step;
     const int cur = step & 1, nxt = cur ^ 1;
@@ -168,14 +201,17 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     float* h_nxt = h_s + nxt * BS * H;
     const uint32_t par = ((step - 1) >> 1) & 1;
 #ifdef B200RNN_TRACE
-    const bool tr = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
+    const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0;  // one row of 8 stamps per (step, warp)
 #else
     constexpr bool tr = false;  // build with -DB200RNN_TRACE for the per-phase clock64 timeline (tools/trace_rec.py)
 #endif
-    long long* trow = p.trace + (size_t)step * 8;
+    long long* trow = p.trace + ((size_t)step * 8 + (w & 7)) * 8;
     if (tr) trow[0] = clock64();
 
-    constexpr bool PACK2 = (MODE == B200RNN_GRU) && RG < 2;  // FFMA2 only where the register budget allows it
+    // FFMA2 (two fp32 FMAs per issue slot; scalar FFMA retires one per two cycles and SMSP) wherever the packed
+    // accumulators fit the register file: the GRU (3 gates) and the LSTM with H = 128 (4 gates, but only 32 resident
+    // weight registers)
+    constexpr bool PACK2 = ((MODE == B200RNN_GRU) || H == 128) && RG < 2;
     float2 acc2[PACK2 ? G : 1][UPL][BS];
     float acc[G][UPL][BS];
 #pragma unroll
@@ -200,22 +236,23 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
           for (int s2 = 0; s2 < Cfg::SPC; ++s2) ptx::mbar_wait(&bars[1 + cur * C + ca * Cfg::SPC + s2], par);
         }
       }
-      if (tr && c == NCH - 1) trow[1] = clock64();  // all slices of h_step have arrived
+      if (tr && c < 4) trow[1 + c] = clock64();     // slice of chunk c has arrived (this warp passed its wait)
       if constexpr (PACK2)
         dots_chunk2<G, RG, KL, UPL, BS, H, H>(W_s, HS, w * UPW, wreg, h_cur, c, ca, lane, acc2);
       else
         dots_chunk<G, RG, KL, UPL, BS, H, H>(W_s, HS, w * UPW, wreg, h_cur, c, ca, lane, acc);
+      if (c == 0 && step > 0) flush_pending(dir ? (T - step) : (step - 1));  // the previous step's stores
     }
-    if (tr) trow[2] = clock64();
     // every slice of h_step has been consumed by this thread => the barriers of the other buffer are re-armed
     if (tid == 0 && step + 1 < T) {
 #pragma unroll
       for (int src = 0; src < C; ++src)
-        ptx::mbar_arrive_expect_tx(&bars[1 + nxt * C + src], (uint32_t)(BS * HS * sizeof(float)));
+        if ((uint32_t)src != rank)
+          ptx::mbar_arrive_expect_tx(&bars[1 + nxt * C + src], (uint32_t)(BS * HS * sizeof(float)));
     }
     if constexpr (PACK2) fold_pairs<G, UPL, BS>(acc2, acc);
     warp_transpose_reduce<G, KL, UPL, BS>(acc);
-    if (tr) trow[3] = clock64() + (long long)(acc[0][0][0] == 12345.678f);  // value dependence pins the order
+    if (tr) trow[5] = clock64() + (long long)(acc[0][0][0] == 12345.678f);  // butterfly done (value dependence pins it)
 
     float hnew, s0, s1, s2, s3 = 0.f, sx;
     if (MODE == B200RNN_GRU) {
@@ -250,23 +287,17 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
       if (t >= len_b) yv = 0.f;
     }
     h_sum += yv;
-    if (tr) trow[4] = clock64() + (long long)(hnew == 12345.678f);
+    if (tr) trow[6] = clock64() + (long long)(hnew == 12345.678f);          // gate math done
 
     if (step + 1 < T)
-      allgather_units<C, KL, UPL, BS>(hnew, h_nxt, H, j0 + w * UPW, &bars[1 + nxt * C + rank], lane);
-    if (tr) trow[5] = clock64();
+      allgather_units<C, KL, UPL, BS, true>(hnew, h_nxt, H, j0 + w * UPW, &bars[1 + nxt * C + rank], lane, rank);
+    if (tr) trow[7] = clock64();                                            // exchange issued
 
-    // off the critical path: global stores of this step, prefetch of the next step's x-projection
+    // prefetch of the next step's x-projection (long latency, consumed at the next gate math); this step's global
+    // stores wait in registers until the next step's first chunk has been issued
+    pend_y = yv; pend_s0 = s0; pend_s1 = s1; pend_s2 = s2; pend_s3 = s3; pend_sx = sx;
+    if (step == T - 1) flush_pending(t);
     if (valid) {
-      if (p.y) p.y[(long long)t * p.y_st + (long long)b * p.y_sb + dir * H + j] = yv;
-      if (p.training) {
-        float* gp = gates + ((size_t)t * B + b) * GH + j;
-        gp[0] = s0;
-        gp[H] = s1;
-        gp[2 * H] = s2;
-        if (G == 4) gp[3 * H] = s3;
-        extra[((size_t)t * B + b) * H + j] = sx;
-      }
       if (step == T - 1) {
         p.h_n[((size_t)dir * B + b) * H + j] = hnew;
         if (p.y_pool) p.y_pool[(size_t)b * p.D * H + dir * H + j] = h_sum;
@@ -471,11 +502,14 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     const uint32_t par = (step >> 1) & 1;
 
     // ---- dh_{prev}[b][j] = direct + sum_col dgh[b][col] * W_hh[col][j], one gate block of columns at a time ----
+    // FFMA2: even-k / odd-k partial sums in one float2 accumulator (one issue slot per two FMAs), folded before the
+    // butterfly - the scalar FFMA pipe retires one warp instruction per two cycles and SMSP
+    float2 acc2[1][UPL][BS];
     float acc[1][UPL][BS];
 #pragma unroll
     for (int au = 0; au < UPL; ++au)
 #pragma unroll
-      for (int ab = 0; ab < BS; ++ab) acc[0][au][ab] = 0.f;
+      for (int ab = 0; ab < BS; ++ab) acc2[0][au][ab] = make_float2(0.f, 0.f);
     // chunk by chunk over the source CTAs (own slice first); a source's G gate-gradient slices share one barrier
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
@@ -489,12 +523,13 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         if (g < NSM)
-          dots_chunk<1, 0, KL, UPL, BS, H, GH>(W_s + (size_t)g * HS * H, 0, w * UPW, wreg, d_buf + g * H, c, ca,
-                                               lane, acc);
+          dots_chunk2<1, 0, KL, UPL, BS, H, GH>(W_s + (size_t)g * HS * H, 0, w * UPW, wreg, d_buf + g * H, c, ca,
+                                                lane, acc2);
         else
-          dots_chunk<1, 1, KL, UPL, BS, H, GH>(W_s, 0, 0, wreg, d_buf + g * H, c, ca, lane, acc);
+          dots_chunk2<1, 1, KL, UPL, BS, H, GH>(W_s, 0, 0, wreg, d_buf + g * H, c, ca, lane, acc2);
       }
     }
+    fold_pairs<1, UPL, BS>(acc2, acc);
     warp_transpose_reduce<1, KL, UPL, BS>(acc);
     dh_carry = direct + acc[0][0][0];
   }

@@ -78,7 +78,8 @@ class FusedFuseStep:
 
     Data parallel (``torch.distributed`` initialised, world > 1): ``exchange="peer"`` (default when CUDA IPC peer
     mapping works) sums the 3 KB gradient inside the same kernel through peer-mapped buffers over NVLink
-    (:class:`b200rnn.dp.PeerComm`); ``exchange="nccl"`` keeps the separate ``all_reduce`` + ``b200rnn_adamw`` launches.
+    (:class:`b200rnn.dp.PeerComm`); ``exchange="nccl"`` keeps the separate ``all_reduce`` + ``b200rnn_adamw`` launches;
+    ``exchange="none"`` runs a single-replica step even when a process group exists.
     """
 
     def __init__(self, model, lr: float = 8e-6, betas=(0.9, 0.999), eps: float = 1e-8, bucket=None,
@@ -114,9 +115,11 @@ class FusedFuseStep:
         self.rng_state = torch.tensor([(torch.initial_seed() * 2654435761 + 12345) & 0x7FFFFFFFFFFFFFFF, 0],
                                       dtype=torch.int64, device=dev)
         self.comm = None
-        if exchange not in ("auto", "peer", "nccl"):
-            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        if exchange not in ("auto", "peer", "nccl", "none"):
+            raise ValueError("exchange must be 'auto', 'peer', 'nccl' or 'none'")
         self.exchange = "none"
+        if exchange == "none":        # single-replica step even inside an initialised process group (no collective)
+            self.world, self.rank = 1, 0
         if self.world > 1:
             self.exchange = "nccl"
             if exchange in ("auto", "peer"):

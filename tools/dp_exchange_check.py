@@ -77,8 +77,7 @@ def main():
     res["graph_vs_eager_max_abs"] = (w_graph - w_peer).abs().max().item()
     if rank == 0:
         m = copy.deepcopy(base)
-        st = b200rnn.FusedFuseStep(m, lr=lr, exchange="auto", process_group=None)
-        st.world, st.exchange = 1, "none"      # single-GPU replay of the global batch
+        st = b200rnn.FusedFuseStep(m, lr=lr, exchange="none")      # single-GPU replay of the global batch
         for s in range(steps):
             st(b200rnn.FuseBatch(audio[s].to(dev), text[s].to(dev)), labels[s].to(dev))
         torch.cuda.synchronize()

@@ -312,8 +312,35 @@ def _time_module_train(kind: str, dev, iters: int = 20, warmup: int = 5) -> dict
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    return {"fwd_bwd_ms_per_batch": ms, "sequences_per_s": 64 / ms * 1e3,
-            "mode": mode + ", train mode (dropout on), dx computed, full model incl. loss"}
+    res = {"fwd_bwd_ms_per_batch": ms, "sequences_per_s": 64 / ms * 1e3,
+           "mode": mode + ", train mode (dropout on), dx computed, full model incl. loss"}
+    del run
+    # the whole train() body of the script (audio_gru_whole.py:161-201): zero_grad -> forward -> Softmax+CE ->
+    # backward (dx too) -> AdamW with the reference's two parameter groups, one CUDA graph (b200rnn.TrainStep)
+    try:
+        lr = cfg["learning_rate"]
+        opt = b200rnn.FlatAdamW.like_reference(model, lr=lr, weight_decay=1e-5)
+        ts = b200rnn.TrainStep(model, opt, tuple(x.shape))
+        ts.warmup_and_capture()
+        xs, ys = x.detach(), y
+        for _ in range(warmup):
+            ts.step(xs, ys)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            ts.step(xs, ys)
+        e1.record()
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / iters
+        res["train_step_ms_per_batch"] = ms2
+        res["train_step_sequences_per_s"] = 64 / ms2 * 1e3
+        res["train_step_mode"] = ("b200rnn.TrainStep: zero_grad + fwd + fused Softmax/CrossEntropy + bwd + FlatAdamW "
+                                  "(2 groups, wd 1e-5 / 0) in one CUDA graph; includes the input copy into the graph's "
+                                  "static buffers; final loss %.6f" % float(ts.loss_value.item()))
+    except Exception as exc:  # noqa: BLE001
+        _log(f"{kind}: TrainStep timing failed: {type(exc).__name__}: {exc}")
+        torch.cuda.synchronize()
+    return res
 
 
 def _parity_check(model, fused, dev) -> dict:
@@ -642,6 +669,14 @@ def run_ours(args) -> None:
                 "final_loss": final_loss},
     }
 
+    finetune = None
+    if not args.quick:   # every rank: the fine-tune variant all-reduces its 10.46 MB gradient bucket
+        try:
+            finetune = _finetune_variant(dev, world)
+            _log(f"fine-tune variant: {finetune['ms_per_step']:.3f} ms/step")
+        except Exception as exc:  # noqa: BLE001
+            _log(f"fine-tune variant failed: {type(exc).__name__}: {exc}")
+            finetune = {"error": f"{type(exc).__name__}: {exc}"}
     if rank == 0:
         line["clocks"] = clocks
         line["parity"] = parity
@@ -690,12 +725,12 @@ def run_ours(args) -> None:
         # ---- secondary module configs (fwd+bwd ms/batch) and the end-to-end fine-tune variant -----------
         _log(f"roofline pass: rec launch {t_launch * 1e3:.3f} ms x{rec_n}")
         extra = {}
-        # single-process only: this block runs on rank 0 alone, and the fine-tune variant all-reduces its gradient
-        # bucket - entered by one rank of several it would wait for peers that are already at the final barrier
+        if finetune is not None:
+            extra["c4_finetune_all_grads_B128_per_gpu"] = finetune
+        # rank-0-only block: nothing in here may contain a collective
         if not args.quick and world == 1:
             extra["c2_audio_gru_whole_train_B64_T120"] = _time_module_train("c2", dev)
             extra["c3_text_bilstm_whole_train_B64_T30_H256"] = _time_module_train("c3", dev)
-            extra["c4_finetune_all_grads_B128"] = _finetune_variant(dev)
             extra["cudnn_comparator"] = _cudnn_comparator(dev)
         line["extra"] = extra
         _log("extras done: " + json.dumps(extra)[:400])
@@ -748,40 +783,42 @@ def _teardown(graphs, e2e_graphs, world: int, fused=None) -> None:
     sys.stderr.flush()
 
 
-def _finetune_variant(dev, iters: int = 10, warmup: int = 3) -> dict:
-    """fuse step with every parameter trainable and the encoders inside autograd: exercises
-    the BPTT kernels and a 10.46 MB gradient bucket. Eager launches."""
+def _finetune_variant(dev, world: int, iters: int = 20, warmup: int = 5) -> dict:
+    """fuse step with every parameter trainable and the encoders inside autograd: BiLSTM + GRU
+    forward and BPTT kernels, ONE all-reduce of the 10.46 MB gradient bucket, Adam - one CUDA graph
+    (b200rnn.FuseFineTuneStep). Entered by EVERY rank (it contains a collective); time = max over ranks."""
     import b200rnn
 
     torch.manual_seed(0)
     model = b200rnn.fusion_net(**FUSE_ARGS).to(dev).train()
-    bucket = b200rnn.GradBucket(model)
-    opt = torch.optim.Adam(model.parameters(), lr=LR, capturable=True)
-    crit = b200rnn.MyLoss(text_hidden_dims=H_TEXT)
-    audio, text, labels = [t.to(dev) for t in _synthetic(B_PER_GPU, 99)]
-
-    def step():
-        bucket.zero()
-        seq, (h_n, _) = model.lstm_net(text.permute(1, 0, 2))
-        tf = model.fc_out(b200rnn.attention_pool(model.attention_layer, seq.permute(1, 0, 2), h_n.permute(1, 0, 2)))
-        af = model.fc_audio(model.lstm_net_audio(model.ln(audio))[0].sum(dim=1))
-        loss = crit(tf, af, labels, model)
-        loss.backward()
-        bucket.allreduce()
-        opt.step()
-
+    b200rnn.broadcast_parameters(model)
+    opt = b200rnn.FlatAdamW([{"params": list(model.parameters()), "weight_decay": 0.0}], lr=LR, model=model)
+    step = b200rnn.FuseFineTuneStep(model, opt, B_PER_GPU, T_AUDIO, T_TEXT)
+    rank = int(os.environ.get("RANK", "0"))
+    audio, text, labels = [t.to(dev) for t in _synthetic(B_PER_GPU, 99 + rank)]
+    mode = "CUDA graph"
+    try:
+        step.warmup_and_capture()
+    except Exception as exc:  # noqa: BLE001
+        _log(f"fine-tune variant: graph capture failed ({type(exc).__name__}: {exc}); eager")
+        torch.cuda.synchronize()
+        step.use_graph, mode = False, "eager"
     for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
+        step.step(audio, text, labels)
+    _barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        step()
+        step.step(audio, text, labels)
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    return {"ms_per_step": ms, "sequences_per_s": B_PER_GPU / ms * 1e3, "grad_bucket_bytes": bucket.nbytes,
-            "mode": "eager; RNN fwd+bwd through the BPTT kernels, all 2,614,016 parameters trainable"}
+    _barrier()
+    ms = _max_over_ranks(e0.elapsed_time(e1), dev) / iters
+    out = {"ms_per_step": ms, "sequences_per_s": B_PER_GPU * world / ms * 1e3, "n_gpus": world,
+           "grad_bucket_bytes": opt.nbytes, "allreduce": "one ncclAllReduce over the flat bucket" if world > 1 else "none",
+           "final_loss": float(step.loss_value.item()),
+           "mode": mode + "; RNN fwd+bwd through the BPTT kernels, all 2,614,016 parameters trainable, FlatAdamW (Adam)"}
+    step.graph = None
+    return out
 
 
 def main() -> None:

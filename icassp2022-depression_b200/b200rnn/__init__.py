@@ -13,9 +13,12 @@ from .dp import GradBucket, broadcast_parameters, shard_batch
 from .models import AudioBiLSTM, MyLoss, TextBiLSTM, attention_pool, fusion_net
 from .fused_head import FusedFuseStep
 from .optim import FlatAdamW
+from .train_step import FuseFineTuneStep, TrainStep, softmax_cross_entropy
+from .dp import PeerComm
 
 __all__ = [
     "GRU", "LSTM", "install", "uninstall", "from_torch", "rnn_forward", "gemm", "RNNConfig", "B200RNNError",
     "AudioBiLSTM", "TextBiLSTM", "fusion_net", "MyLoss", "attention_pool", "FuseBatch", "PinnedStager",
     "stage_fuse_batch", "GradBucket", "broadcast_parameters", "shard_batch", "FusedFuseStep", "FlatAdamW",
+    "TrainStep", "FuseFineTuneStep", "softmax_cross_entropy", "PeerComm",
 ]

@@ -35,6 +35,7 @@ SYMBOLS = (
     "b200rnn_mlp_dropout",
     "b200rnn_rng_next",
     "b200rnn_fuse_loss_grad",
+    "b200rnn_softmax_ce",
     "b200rnn_adam",
     "b200rnn_adamw",
     "b200rnn_fuse_head",
@@ -179,6 +180,8 @@ def load() -> ctypes.CDLL:
     lib.b200rnn_fuse_loss_grad.restype = c_int
     lib.b200rnn_fuse_loss_grad.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                            c_void_p, c_void_p, c_void_p]
+    lib.b200rnn_softmax_ce.restype = c_int
+    lib.b200rnn_softmax_ce.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.b200rnn_adam.restype = c_int
     lib.b200rnn_adam.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
                                  c_float, c_void_p]

@@ -84,14 +84,21 @@ class AudioBiLSTM(nn.Module):
         self.fc_audio = nn.Sequential(nn.Dropout(p), nn.Linear(H, H), nn.ReLU(), nn.Dropout(p),
                                       nn.Linear(H, self.num_classes), *tail)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if self.regression:                          # audio_bilstm_perm.py:122-127
+    def pooled(self, x: torch.Tensor) -> torch.Tensor:
+        """[LayerNorm ->] GRU -> mean / sum over time, [B, H]."""
+        if self.regression:                          # audio_bilstm_perm.py:122-125
             seq, _ = self.lstm_net_audio(x)
-            pooled = seq.sum(dim=1)
-        else:                                        # audio_gru_whole.py:103-108
-            seq, _ = self.lstm_net_audio(self.ln(x))
-            pooled = seq.mean(dim=1)
-        return self.fc_audio(pooled)
+            return seq.sum(dim=1)
+        seq, _ = self.lstm_net_audio(self.ln(x))     # audio_gru_whole.py:103-106
+        return seq.mean(dim=1)
+
+    def forward_logits(self, x: torch.Tensor) -> torch.Tensor:
+        """``forward`` without the final activation (the input of the model's Softmax / ReLU): what a fused
+        softmax + cross-entropy loss consumes (b200rnn.train_step)."""
+        return self.fc_audio[:-1](self.pooled(x))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.fc_audio(self.pooled(x))
 
 
 class TextBiLSTM(nn.Module):
@@ -130,11 +137,17 @@ class TextBiLSTM(nn.Module):
     def attention_net_with_w(self, lstm_out: torch.Tensor, lstm_hidden: torch.Tensor) -> torch.Tensor:
         return attention_pool(self.attention_layer, lstm_out, lstm_hidden)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def context(self, x: torch.Tensor) -> torch.Tensor:
         # [B,T,E] -> time-major NON-contiguous view, consumed in place by the kernels (text_bilstm_whole.py:103)
         seq, (h_n, _) = self.lstm_net(x.permute(1, 0, 2))
-        ctx = attention_pool(self.attention_layer, seq.permute(1, 0, 2), h_n.permute(1, 0, 2))
-        return self.fc_out(ctx)
+        return attention_pool(self.attention_layer, seq.permute(1, 0, 2), h_n.permute(1, 0, 2))
+
+    def forward_logits(self, x: torch.Tensor) -> torch.Tensor:
+        """``forward`` without the final activation (see AudioBiLSTM.forward_logits)."""
+        return self.fc_out[:-1](self.context(x))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.fc_out(self.context(x))
 
 
 class fusion_net(nn.Module):  # noqa: N801  (reference class name)

@@ -19,13 +19,14 @@ from .modules import _B200RNNBase
 
 
 class _Group:
-    def __init__(self, params: List[torch.nn.Parameter], weight_decay: float):
+    def __init__(self, params: List[torch.nn.Parameter], weight_decay: float, flat_g: torch.Tensor):
         self.params = params
         self.weight_decay = float(weight_decay)
         dev = params[0].device
         offs, n = _aligned_offsets(params)     # 256-byte aligned views: weight_hh feeds TMA bulk copies
+        assert flat_g.numel() == n
         self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_g = flat_g                   # a slice of the optimiser-wide gradient bucket (ONE all-reduce per step)
         self.m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
         self.views = []
@@ -48,9 +49,18 @@ class FlatAdamW:
     def __init__(self, groups: Sequence[dict], lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
                  model: Optional[torch.nn.Module] = None, process_group=None):
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
-        self.groups = [_Group([p for p in g["params"] if p.requires_grad], g.get("weight_decay", 0.0))
-                       for g in groups if any(p.requires_grad for p in g["params"])]
-        dev = self.groups[0].flat_p.device
+        plist = [([p for p in g["params"] if p.requires_grad], g.get("weight_decay", 0.0))
+                 for g in groups if any(p.requires_grad for p in g["params"])]
+        dev = plist[0][0][0].device
+        sizes = [(_aligned_offsets(ps)[1] + 63) // 64 * 64 for ps, _ in plist]
+        # every group's gradients live in ONE contiguous bucket: the data-parallel step all-reduces it with a single
+        # collective, the per-group AdamW launches read their slice of it
+        self.bucket = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.groups, off = [], 0
+        for (ps, wd), n_al in zip(plist, sizes):
+            n = _aligned_offsets(ps)[1]
+            self.groups.append(_Group(ps, wd, self.bucket[off:off + n]))
+            off += n_al
         self.step_count = torch.zeros((), dtype=torch.float32, device=dev)
         self.process_group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -99,15 +109,18 @@ class FlatAdamW:
 
     def zero_grad(self, set_to_none: bool = False) -> None:   # the views are the optimiser's own storage: never dropped
         self.reattach()
-        for g in self.groups:
-            g.flat_g.zero_()
+        self.bucket.zero_()
 
     def allreduce(self) -> None:
-        """One collective per group (the reference's two groups could be merged; kept separate for clarity)."""
+        """The step's single collective: one all-reduce over the bucket that holds every group's gradients (the 1/world
+        of the mean is folded into the AdamW kernel)."""
         self.reattach()
         if self.world > 1:
-            for g in self.groups:
-                dist.all_reduce(g.flat_g, op=dist.ReduceOp.SUM, group=self.process_group)
+            dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM, group=self.process_group)
+
+    @property
+    def nbytes(self) -> int:
+        return self.bucket.numel() * 4
 
     @torch.no_grad()
     def step(self) -> None:

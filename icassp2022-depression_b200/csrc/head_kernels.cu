@@ -233,6 +233,52 @@ __global__ void __launch_bounds__(LOSS_THREADS)
   }
 }
 
+// ---- CrossEntropyLoss applied to Softmax OUTPUTS, forward + backward in one pass -------------------------------------
+// The classification scripts end their models with nn.Softmax and then feed the probabilities to nn.CrossEntropyLoss
+// (audio_gru_whole.py:73, 188, 308; text_bilstm_whole.py:68, 180, 304), i.e. loss = mean_b( -log softmax(p_b)[y_b] ) with
+// p = softmax(z). One warp per row: p, the row loss, and d loss / d z (chain rule through both softmaxes):
+//   q = softmax(p);  g = (q - onehot(y)) / B;  dz = p * (g - sum_c p_c g_c)
+constexpr int SCE_MAXC = 32;
+__global__ void softmax_ce_kernel(const float* __restrict__ z, const long long* __restrict__ labels, int B, int C,
+                                  float* __restrict__ probs, float* __restrict__ dz, float* __restrict__ row_loss) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float NEG = -INFINITY;
+  const float zv = lane < C ? z[(size_t)row * C + lane] : NEG;
+  float m = warp_max(zv);
+  float e = lane < C ? expf(zv - m) : 0.f;
+  const float p = e / warp_sum(e);                       // model output (Softmax)
+  const float pv = lane < C ? p : NEG;
+  m = warp_max(pv);
+  e = lane < C ? expf(pv - m) : 0.f;
+  const float se = warp_sum(e);
+  const float q = e / se;                                // softmax of the probabilities (inside CrossEntropyLoss)
+  const long long y = labels[row];
+  const float py = __shfl_sync(0xffffffffu, pv, (int)(y >= 0 && y < C ? y : 0));
+  float loss = (m + logf(se)) - py;
+  if (y < 0 || y >= C) loss = __int_as_float(0x7fc00000);  // a label outside [0, C) poisons the loss
+  const float g = lane < C ? (q - (lane == (int)y ? 1.f : 0.f)) / (float)B : 0.f;
+  const float dot = warp_sum(lane < C ? p * g : 0.f);
+  if (lane < C) {
+    probs[(size_t)row * C + lane] = p;
+    dz[(size_t)row * C + lane] = p * (g - dot);
+  }
+  if (lane == 0) row_loss[row] = loss;
+}
+__global__ void mean_rows_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  __shared__ float part[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];  // fixed order per thread => deterministic
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) *out = s / (float)n;
+  }
+}
+
 // ---- Adam (torch.optim.Adam defaults: no weight decay, no amsgrad), step counter on the device ------------------
 // weight_decay is decoupled (torch.optim.AdamW: p *= 1 - lr*wd before the update; 0 gives torch.optim.Adam);
 // grad_scale folds the 1/world averaging of the data-parallel all-reduce into the same pass.
@@ -330,6 +376,26 @@ B200RNN_API int b200rnn_fuse_loss_grad(const float* text_feature, int Ht, const 
       text_feature, Ht, audio_feature, Ha, reinterpret_cast<const long long*>(labels), B, W, dW, accumulate, loss, probs);
   B200_CUDA_CHECK(cudaGetLastError());
   count_launch();
+  return B200RNN_OK;
+}
+
+B200RNN_API int b200rnn_softmax_ce(const float* logits, const int64_t* labels, int B, int C, float* probs, float* dlogits,
+                                   float* row_loss, float* loss, void* stream_) {
+  if (!logits || !labels || !probs || !dlogits || !row_loss || !loss || B < 1 || C < 1) {
+    set_error("softmax_ce: bad argument");
+    return B200RNN_ERR_INVALID;
+  }
+  if (C > SCE_MAXC) {
+    set_error("softmax_ce: %d classes > %d unsupported", C, SCE_MAXC);
+    return B200RNN_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  softmax_ce_kernel<<<(B + 7) / 8, 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), B, C, probs, dlogits,
+                                               row_loss);
+  B200_CUDA_CHECK(cudaGetLastError());
+  mean_rows_kernel<<<1, 256, 0, st>>>(row_loss, B, loss);
+  B200_CUDA_CHECK(cudaGetLastError());
+  count_launch(2);
   return B200RNN_OK;
 }
 

@@ -202,6 +202,11 @@ B200RNN_API int b200rnn_rng_next(uint64_t* rng_hdr, uint64_t* rng_state, uint64_
 B200RNN_API int b200rnn_fuse_loss_grad(const float* text_feature, int Ht, const float* audio_feature, int Ha,
                                        const int64_t* labels, int B, const float* W, float* dW, int accumulate,
                                        float* loss, float* probs, void* stream);
+/* CrossEntropyLoss on Softmax OUTPUTS, as the classification scripts compute it (audio_gru_whole.py:73,188,308;
+ * text_bilstm_whole.py:68,180,304): probs = softmax(logits) [B,C]; loss = mean_b -log softmax(probs_b)[y_b]; and
+ * dlogits = d loss / d logits through both softmaxes, all in one pass (C <= 32). row_loss [B] is scratch. */
+B200RNN_API int b200rnn_softmax_ce(const float* logits, const int64_t* labels, int B, int C, float* probs, float* dlogits,
+                                   float* row_loss, float* loss, void* stream);
 B200RNN_API int b200rnn_adam(float* p, const float* g, float* m, float* v, float* step, size_t n, float lr,
                              float beta1, float beta2, float eps, void* stream);
 /* AdamW over one flat parameter group (audio_gru_whole.py:247-255, 307: optim.AdamW with a decay and a no-decay group):

@@ -1,8 +1,8 @@
 """Static checks of bench.py's multi-rank control flow (no GPU needed).
 
-Regression guard: the secondary timings run inside the rank-0-only block; `_finetune_variant` all-reduces a gradient
-bucket, so entered by one rank of a torchrun launch it dead-locks against the peers' final barrier (observed once at
-N=2, 600 s). They must stay behind a `world == 1` condition.
+Regression guard: `_finetune_variant` all-reduces a gradient bucket. Round 1 called it from the rank-0-only block and
+a torchrun launch dead-locked against the peers' final barrier (observed once at N=2, 600 s). It is now entered by
+EVERY rank, so it must never sit under a rank condition; the remaining rank-0-only extras must stay collective-free.
 """
 import ast
 import os
@@ -14,17 +14,22 @@ def _calls(node, name):
     return [n for n in ast.walk(node) if isinstance(n, ast.Call) and getattr(n.func, "id", None) == name]
 
 
-def test_rank0_only_extras_are_single_process_only():
+def test_finetune_variant_is_entered_by_every_rank():
     src = open(os.path.join(ROOT, "bench.py")).read()
     tree = ast.parse(src)
     run_ours = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "run_ours")
-    guarded = []
+    assert _calls(run_ours, "_finetune_variant"), "bench.py no longer calls _finetune_variant from run_ours?"
     for node in ast.walk(run_ours):
         if isinstance(node, ast.If) and _calls(node, "_finetune_variant"):
-            guarded.append(ast.get_source_segment(src, node.test))
-    assert guarded, "bench.py no longer calls _finetune_variant from run_ours?"
-    innermost = min(guarded, key=len)
-    assert any("world == 1" in g for g in guarded), f"extras not restricted to one process: {innermost}"
+            test = ast.get_source_segment(src, node.test)
+            assert "rank" not in test and "world == 1" not in test, f"_finetune_variant under a rank condition: {test}"
+    # the helpers that only rank 0 runs must not reach a collective themselves
+    for fn in ("_time_module_train", "_cudnn_comparator", "_parity_check"):
+        node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == fn)
+        for n in ast.walk(node):
+            if isinstance(n, ast.Attribute) and n.attr in ("barrier", "all_reduce", "broadcast"):
+                raise AssertionError(f"collective `{n.attr}` inside rank-0-only helper {fn} (line {n.lineno})")
+        assert not _calls(node, "_barrier") and not _calls(node, "_max_over_ranks"), fn
 
 
 def test_collectives_in_run_ours_are_not_under_rank_conditions():

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("B200RNN_LIB") or os.path.join(os.path.dirname(_HERE),
 GRU, LSTM = 0, 1
 FLAG_ACCUMULATE_GRADS = 1
 FLAG_SAVE_FOR_BACKWARD = 2
+FLAG_FUSED_LN = 4
 ABI_VERSION = 2
 
 # every symbol include/b200rnn.h declares (tests check the .so exports exactly these)
@@ -28,6 +29,7 @@ SYMBOLS = (
     "b200rnn_forward",
     "b200rnn_forward_fused",
     "b200rnn_backward",
+    "b200rnn_backward_fused",
     "b200rnn_wcache_bytes",
     "b200rnn_prepare_weights",
     "b200rnn_gemm_f32",
@@ -162,6 +164,21 @@ def load() -> ctypes.CDLL:
         c_void_p, c_int64, c_int64,                  # dx
         POINTER(c_void_p),                           # dparams
         c_void_p,                                    # lengths
+        c_void_p,                                    # stream
+    ]
+    lib.b200rnn_backward_fused.restype = c_int
+    lib.b200rnn_backward_fused.argtypes = [
+        POINTER(Desc), c_void_p, c_int64, c_int64,   # desc, x, strides
+        POINTER(c_void_p),                           # params
+        c_void_p, c_int64, c_int64,                  # y
+        c_void_p, c_int64, c_int64,                  # dy
+        c_void_p, c_float,                           # dy_pool, dy_pool_scale
+        c_void_p, c_void_p,                          # dh_n, dc_n
+        c_void_p, c_void_p,                          # reserve, scratch
+        c_void_p, c_int64, c_int64,                  # dx
+        POINTER(c_void_p),                           # dparams
+        c_void_p,                                    # lengths
+        c_void_p, c_float, c_void_p, c_void_p,       # ln_gamma, ln_eps, dln_gamma, dln_beta
         c_void_p,                                    # stream
     ]
     lib.b200rnn_gemm_f32.restype = c_int

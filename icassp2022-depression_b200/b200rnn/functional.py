@@ -44,12 +44,15 @@ def _tm_view(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
-def _make_desc(cfg: RNNConfig, B: int, T: int, save: bool, accumulate: bool = False) -> _lib.Desc:
+def _make_desc(cfg: RNNConfig, B: int, T: int, save: bool, accumulate: bool = False,
+               fused_ln: bool = False) -> _lib.Desc:
     flags = 0
     if save:
         flags |= _lib.FLAG_SAVE_FOR_BACKWARD
     if accumulate:
         flags |= _lib.FLAG_ACCUMULATE_GRADS
+    if fused_ln:
+        flags |= _lib.FLAG_FUSED_LN
     return _lib.Desc(cfg.mode, B, T, cfg.input_size, cfg.hidden_size, cfg.num_layers, cfg.num_dirs,
                      1 if cfg.training else 0, float(cfg.dropout), flags)
 
@@ -188,6 +191,114 @@ class _RNNFunction(torch.autograd.Function):
                 if g is not None:
                     g.zero_()
         return (dx, None, None, None, None, None, *grads_out)
+
+
+class _LNRNNPoolFunction(torch.autograd.Function):
+    """pooled[B, D*H] = sum over time of RNN(LayerNorm(x)) with everything around the encoder fused IN THE TRAINING
+    GRAPH: LayerNorm folded into the operand preparation of the layer-0 projection (forward) and
+    run backwards inside ``b200rnn_backward_fused``; the time sum accumulated in the recurrence epilogue; and the pooled
+    gradient broadcast over the steps inside the BPTT kernel - neither ``LN(x)`` as an autograd tensor nor the
+    ``[T,B,D*H]`` output gradient ever exist. ``x.mean(dim=1)`` is this sum times 1/T (a [B,H] op left to autograd).
+    """
+
+    @staticmethod
+    def forward(ctx, x_tm: torch.Tensor, cfg: RNNConfig, rng_state, grad_sink, ln_w, ln_b, ln_eps: float,
+                *weights: torch.Tensor):
+        lib = _lib.load()
+        T, B, _ = x_tm.shape
+        H, L, D = cfg.hidden_size, cfg.num_layers, cfg.num_dirs
+        dev = x_tm.device
+        fused_ln = ln_w is not None
+        desc = _make_desc(cfg, B, T, True, fused_ln=fused_ln)
+        rbytes, sbytes = _lib.workspace_bytes(desc)
+        reserve = torch.empty(rbytes, dtype=torch.uint8, device=dev)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+        y = torch.empty(T, B, D * H, dtype=torch.float32, device=dev)     # h_t of the top layer: BPTT needs h_{t-1}
+        pooled = torch.empty(B, D * H, dtype=torch.float32, device=dev)
+        h_n = torch.empty(L * D, B, H, dtype=torch.float32, device=dev)
+        c_n = torch.empty(L * D, B, H, dtype=torch.float32, device=dev) if cfg.mode == _lib.LSTM else None
+        params = _lib.ptr_array([w.data_ptr() for w in weights])
+        with _on(dev):
+            rc = lib.b200rnn_forward_fused(
+                ctypes.byref(desc), x_tm.data_ptr(), x_tm.stride(0), x_tm.stride(1), params,
+                y.data_ptr(), B * D * H, D * H, h_n.data_ptr(), c_n.data_ptr() if c_n is not None else None,
+                reserve.data_ptr(), scratch.data_ptr(), 0, 0,
+                rng_state.data_ptr() if rng_state is not None else None,
+                ln_w.data_ptr() if fused_ln else None, ln_b.data_ptr() if fused_ln else None, float(ln_eps),
+                pooled.data_ptr(), None, None, _stream_ptr(dev))
+        _lib.check(rc, "b200rnn_forward_fused")
+        ctx.cfg, ctx.grad_sink, ctx.ln_eps, ctx.fused_ln = cfg, grad_sink, float(ln_eps), fused_ln
+        ctx.save_for_backward(x_tm, y, reserve, ln_w if fused_ln else x_tm.new_empty(0), *weights)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpool):
+        lib = _lib.load()
+        cfg: RNNConfig = ctx.cfg
+        x_tm, y, reserve, ln_w, *weights = ctx.saved_tensors
+        T, B, I = x_tm.shape
+        H, L, D = cfg.hidden_size, cfg.num_layers, cfg.num_dirs
+        dev = x_tm.device
+        dpool = dpool.contiguous()
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty(T, B, I, dtype=torch.float32, device=dev) if need_dx else None
+        dln_w = torch.empty_like(ln_w) if (ctx.fused_ln and ctx.needs_input_grad[4]) else None
+        dln_b = torch.empty_like(ln_w) if (ctx.fused_ln and ctx.needs_input_grad[5]) else None
+        sink = ctx.grad_sink
+        w_needed = [ctx.needs_input_grad[7 + i] for i in range(len(weights))]
+        grads_out: list = [None] * len(weights)
+        accumulate = False
+        if sink is not None:
+            targets = sink(weights)
+            accumulate = True
+            dptrs = [t.data_ptr() if (t is not None and n) else None for t, n in zip(targets, w_needed)]
+        else:
+            sizes = [(w.numel() + 63) // 64 * 64 if n else 0 for w, n in zip(weights, w_needed)]
+            flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            dptrs, off = [], 0
+            for i, (w, n) in enumerate(zip(weights, w_needed)):
+                if n:
+                    g = flat[off:off + w.numel()].view_as(w)
+                    off += sizes[i]
+                    grads_out[i] = g
+                    dptrs.append(g.data_ptr())
+                else:
+                    dptrs.append(None)
+        # with a sink the RNN weight gradients accumulate; the LayerNorm gradients are returned to autograd (fresh
+        # tensors), so they must be WRITTEN: run them through a zeroed target when accumulating
+        if accumulate:
+            if dln_w is not None:
+                dln_w.zero_()
+            if dln_b is not None:
+                dln_b.zero_()
+        desc = _make_desc(cfg, B, T, True, accumulate, fused_ln=ctx.fused_ln)
+        _, sbytes = _lib.workspace_bytes(desc)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+        params = _lib.ptr_array([w.data_ptr() for w in weights])
+        dparams = _lib.ptr_array(dptrs)
+        with _on(dev):
+            rc = lib.b200rnn_backward_fused(
+                ctypes.byref(desc), x_tm.data_ptr(), x_tm.stride(0), x_tm.stride(1), params,
+                y.data_ptr(), B * D * H, D * H, None, 0, 0, dpool.data_ptr(), 1.0, None, None,
+                reserve.data_ptr(), scratch.data_ptr(),
+                dx.data_ptr() if dx is not None else None, B * I if dx is not None else 0, I if dx is not None else 0,
+                dparams, None, ln_w.data_ptr() if ctx.fused_ln else None, ctx.ln_eps,
+                dln_w.data_ptr() if dln_w is not None else None, dln_b.data_ptr() if dln_b is not None else None,
+                _stream_ptr(dev))
+        _lib.check(rc, "b200rnn_backward_fused")
+        return (dx, None, None, None, dln_w, dln_b, None, *grads_out)
+
+
+def rnn_ln_pool_sum(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNNConfig, rng_state=None, grad_sink=None,
+                    ln_weight: Optional[torch.Tensor] = None, ln_bias: Optional[torch.Tensor] = None,
+                    ln_eps: float = 1e-5) -> torch.Tensor:
+    """``RNN(LayerNorm(x))[0].sum(dim=time)`` under autograd with the shell fused around the encoder (see
+    :class:`_LNRNNPoolFunction`). ``x`` is [T,B,I] or [B,T,I] (``cfg.batch_first``); returns [B, D*H]."""
+    _require_cuda_f32(x, "input")
+    for i, w in enumerate(weights):
+        _require_cuda_f32(w, f"weight[{i}]")
+    x_tm = _tm_view(x.transpose(0, 1) if cfg.batch_first else x)
+    return _LNRNNPoolFunction.apply(x_tm, cfg, rng_state, grad_sink, ln_weight, ln_bias, ln_eps, *weights)
 
 
 def rnn_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], cfg: RNNConfig,

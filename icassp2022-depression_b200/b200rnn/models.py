@@ -86,11 +86,10 @@ class AudioBiLSTM(nn.Module):
 
     def pooled(self, x: torch.Tensor) -> torch.Tensor:
         """[LayerNorm ->] GRU -> mean / sum over time, [B, H]."""
-        if self.regression:                          # audio_bilstm_perm.py:122-125
-            seq, _ = self.lstm_net_audio(x)
-            return seq.sum(dim=1)
-        seq, _ = self.lstm_net_audio(self.ln(x))     # audio_gru_whole.py:103-106
-        return seq.mean(dim=1)
+        if self.regression:                          # audio_bilstm_perm.py:122-125: GRU -> sum(dim=1)
+            return self.lstm_net_audio.forward_ln_sum(x, None)
+        # audio_gru_whole.py:103-106: LayerNorm -> GRU -> mean(dim=1); the shell is fused around the encoder
+        return self.lstm_net_audio.forward_ln_sum(x, self.ln) * (1.0 / x.shape[1])
 
     def forward_logits(self, x: torch.Tensor) -> torch.Tensor:
         """``forward`` without the final activation (the input of the model's Softmax / ReLU): what a fused

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import RNNConfig, prepare_weights, rnn_forward, rnn_forward_fused
+from .functional import RNNConfig, prepare_weights, rnn_forward, rnn_forward_fused, rnn_ln_pool_sum
 
 _TORCH_GRU = nn.GRU
 _TORCH_LSTM = nn.LSTM
@@ -183,14 +183,24 @@ class _B200RNNBase(nn.Module):
     def forward_ln_sum(self, input: torch.Tensor, ln: Optional[nn.LayerNorm] = None) -> torch.Tensor:
         """``self(ln(input))[0].sum(dim=time)`` — the audio branch of fuse_net_whole.py:360-362 / fuse_net.py:338-339.
 
-        Without autograd (the reference runs it under ``torch.no_grad()``, fuse_net_whole.py:337) and for widths the
-        tensor-core projection takes, LayerNorm is folded into the layer-0 operand preparation and the time sum into
-        the last layer's step loop, so the normalised input and the [B,T,H] output never touch HBM. Otherwise the same
-        value is computed unfused.
+        For widths the tensor-core projection takes, LayerNorm is folded into the layer-0 operand preparation and the
+        time sum into the last layer's step loop. Without autograd (the reference's fuse scripts run it under
+        ``torch.no_grad()``, fuse_net_whole.py:337) the normalised input and the [B,T,H] output never touch HBM; under
+        autograd (audio_gru_whole.py:103-108 + loss.backward()) the same fusions run in both directions
+        (``b200rnn_backward_fused``: LayerNorm backward, pooled-gradient broadcast inside the BPTT kernel). Otherwise
+        the same value is computed unfused.
         """
-        need_grad = torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters()))
-        fusable = (not need_grad and input.is_cuda and input.dim() == 3 and self.input_size % 128 == 0 and
-                   self.input_size <= 1024 and (ln is None or (ln.elementwise_affine and ln.bias is not None)))
+        need_grad = torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())
+                                                 or (ln is not None and any(p.requires_grad for p in ln.parameters())))
+        shape_ok = (input.is_cuda and input.dim() == 3 and self.input_size % 128 == 0 and self.input_size <= 1024 and
+                    (ln is None or (ln.elementwise_affine and ln.bias is not None)))
+        if need_grad and shape_ok and not isinstance(input, nn.utils.rnn.PackedSequence):
+            # training graph: LayerNorm forward+backward folded around the layer-0 GEMMs, pooled gradient broadcast
+            # inside the BPTT kernel (no [T,B,H] output gradient, no LN(x) autograd tensor)
+            return rnn_ln_pool_sum(input, self._flat_weights, self._config(), self._rng_state, self._grad_sink,
+                                   ln.weight if ln is not None else None, ln.bias if ln is not None else None,
+                                   ln.eps if ln is not None else 1e-5)
+        fusable = not need_grad and shape_ok
         if fusable:
             out = rnn_forward_fused(input, self._flat_weights, self._config(), self._rng_state,
                                     ln.weight if ln is not None else None, ln.bias if ln is not None else None,

@@ -172,8 +172,7 @@ class FuseFineTuneStep(TrainStep):
         self.opt.zero_grad()
         seq, (h_n, _) = m.lstm_net(self.text.permute(1, 0, 2))
         tf = m.fc_out(attention_pool(m.attention_layer, seq.permute(1, 0, 2), h_n.permute(1, 0, 2)))
-        xa = self.x if m.regression else m.ln(self.x)
-        af = m.fc_audio(m.lstm_net_audio(xa)[0].sum(dim=1))
+        af = m.fc_audio(m.lstm_net_audio.forward_ln_sum(self.x, None if m.regression else m.ln))
         out = m(torch.cat((tf, af), dim=1))
         loss = self.criterion(tf, af, self.y, m)
         loss.backward()

@@ -86,10 +86,11 @@ constexpr size_t ALIGN_F = 64;  // floats (256 B)
 struct ReserveLayout {
   size_t gates[8][2], extra[8][2];  // up to 8 layers
   size_t ylayer[8], ydrop[8];
+  size_t xln;  // LayerNorm(x) of the folded prologue, kept for the layer-0 wgrad (B200RNN_FLAG_FUSED_LN)
   size_t total;
 };
 
-int make_reserve(const Dims& d, ReserveLayout* r) {
+int make_reserve(const Dims& d, ReserveLayout* r, bool fused_ln = false) {
   if (d.L > 8) {
     set_error("num_layers %d > 8 unsupported", d.L);
     return B200RNN_ERR_UNSUPPORTED;
@@ -108,6 +109,8 @@ int make_reserve(const Dims& d, ReserveLayout* r) {
     r->ydrop[l] = off;
     if (d.p > 0.f) off += align_up(d.TB * d.DH, ALIGN_F);
   }
+  r->xln = off;
+  if (fused_ln) off += align_up(d.TB * (size_t)d.I, ALIGN_F);
   r->total = off;
   return B200RNN_OK;
 }
@@ -125,6 +128,7 @@ struct ScratchLayout {
   size_t b_tc_dg, b_tc_dgT, b_tc_hnT, b_tc_xT, b_tc_yT, b_tc_wT, b_tc_part;
   size_t b_tc_part_bytes;
   long long b_ldk;  // leading dimension of the transposed operands: T*B rounded up to a multiple of 4
+  size_t b_dxln, b_lnpart;  // fused LayerNorm backward: dense d/dLN(x) [TB][I], per-CTA column partials
   size_t b_total;
 };
 
@@ -184,6 +188,10 @@ void make_scratch(const Dims& d, ScratchLayout* s) {
     s->b_tc_part_bytes = (size_t)160 * 128 * 128 * sizeof(float);  // <= (#SMs / tiles) * M * N
     off += align_up(s->b_tc_part_bytes / sizeof(float), ALIGN_F);
   }
+  s->b_dxln = off;
+  off += align_up(d.TB * (size_t)d.I, ALIGN_F);
+  s->b_lnpart = off;
+  off += align_up(layernorm_bwd_scratch_floats(d.I), ALIGN_F);
   s->b_total = off;
 }
 
@@ -240,7 +248,7 @@ B200RNN_API int b200rnn_workspace_bytes(const b200rnn_desc* desc, size_t* reserv
   int rc = check_desc(desc, &d);
   if (rc) return rc;
   ReserveLayout r;
-  rc = make_reserve(d, &r);
+  rc = make_reserve(d, &r, (desc->flags & B200RNN_FLAG_FUSED_LN) != 0);
   if (rc) return rc;
   ScratchLayout s;
   make_scratch(d, &s);
@@ -272,7 +280,12 @@ B200RNN_API int b200rnn_forward_fused(const b200rnn_desc* desc, const float* x, 
     return B200RNN_ERR_INVALID;
   }
   if (!y && save) {
-    set_error("forward: the full output is needed by backward; pooled-only output requires a no-grad forward");
+    set_error("forward: the full output is needed by backward (h_{t-1} of every step): pass y as well as y_pool");
+    return B200RNN_ERR_INVALID;
+  }
+  const bool fused_ln = (desc->flags & B200RNN_FLAG_FUSED_LN) != 0;
+  if (fused_ln && !ln_gamma) {
+    set_error("forward: B200RNN_FLAG_FUSED_LN without ln_gamma / ln_beta");
     return B200RNN_ERR_INVALID;
   }
   if ((ln_gamma == nullptr) != (ln_beta == nullptr)) {
@@ -292,7 +305,7 @@ B200RNN_API int b200rnn_forward_fused(const b200rnn_desc* desc, const float* x, 
     return B200RNN_ERR_INVALID;
   }
   ReserveLayout rl;
-  rc = make_reserve(d, &rl);
+  rc = make_reserve(d, &rl, fused_ln);
   if (rc) return rc;
   ScratchLayout sl;
   make_scratch(d, &sl);
@@ -329,7 +342,8 @@ B200RNN_API int b200rnn_forward_fused(const b200rnn_desc* desc, const float* x, 
       float* a_hi = tc_a_hi(tc_ws);
       float* a_lo = tc_a_lo(tc_ws, (int)d.TB, Il);
       if (l == 0 && ln_gamma)
-        rc = tc_layernorm_split(in, in_rows, (int)d.TB, Il, ln_gamma, ln_beta, ln_eps, a_hi, a_lo, st);
+        rc = tc_layernorm_split(in, in_rows, (int)d.TB, Il, ln_gamma, ln_beta, ln_eps, a_hi, a_lo, st,
+                                (save && fused_ln) ? R + rl.xln : nullptr);
       else if (!a_ready)
         rc = tc_split(in, in_rows, (int)d.TB, Il, a_hi, a_lo, st);
       if (rc) return rc;
@@ -460,26 +474,37 @@ B200RNN_API int b200rnn_prepare_weights(const b200rnn_desc* desc, const float* c
   return B200RNN_OK;
 }
 
-B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64_t xs_t, int64_t xs_b,
-                                 const float* const* params, const float* y, int64_t ys_t, int64_t ys_b,
-                                 const float* dy, int64_t dys_t, int64_t dys_b, const float* dh_n,
-                                 const float* dc_n, const void* reserve, void* scratch, float* dx, int64_t dxs_t,
-                                 int64_t dxs_b, float* const* dparams, const int32_t* lengths, void* stream_) {
+B200RNN_API int b200rnn_backward_fused(const b200rnn_desc* desc, const float* x, int64_t xs_t, int64_t xs_b,
+                                       const float* const* params, const float* y, int64_t ys_t, int64_t ys_b,
+                                       const float* dy, int64_t dys_t, int64_t dys_b, const float* dy_pool,
+                                       float dy_pool_scale, const float* dh_n, const float* dc_n, const void* reserve,
+                                       void* scratch, float* dx, int64_t dxs_t, int64_t dxs_b, float* const* dparams,
+                                       const int32_t* lengths, const float* ln_gamma, float ln_eps, float* dln_gamma,
+                                       float* dln_beta, void* stream_) {
   Dims d;
   int rc = check_desc(desc, &d);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   if (d.B == 0 || d.T == 0) return B200RNN_OK;
-  if (!x || !params || !y || !dy || !reserve || !scratch || !dparams) {
+  if (!x || !params || !y || (!dy && !dy_pool) || !reserve || !scratch || !dparams) {
     set_error("backward: null pointer argument");
     return B200RNN_ERR_INVALID;
+  }
+  const bool fused_ln = (desc->flags & B200RNN_FLAG_FUSED_LN) != 0;
+  if (fused_ln != (ln_gamma != nullptr)) {
+    set_error("backward: B200RNN_FLAG_FUSED_LN and ln_gamma must be given together (as in the forward)");
+    return B200RNN_ERR_INVALID;
+  }
+  if (fused_ln && (d.I % 128 != 0 || d.I > 1024 || !tc_available())) {
+    set_error("backward: the fused LayerNorm needs input_size in {128,...,1024} (multiple of 128)");
+    return B200RNN_ERR_UNSUPPORTED;
   }
   if (!aligned_to(reserve, 256) || !aligned_to(scratch, 256)) {
     set_error("backward: reserve/scratch must be 256-byte aligned");
     return B200RNN_ERR_INVALID;
   }
   ReserveLayout rl;
-  rc = make_reserve(d, &rl);
+  rc = make_reserve(d, &rl, fused_ln);
   if (rc) return rc;
   ScratchLayout sl;
   make_scratch(d, &sl);
@@ -498,6 +523,7 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
     if (l == d.L - 1) {
       bp.y = y; bp.y_st = ys_t; bp.y_sb = ys_b;
       bp.dy = dy; bp.dy_st = dys_t; bp.dy_sb = dys_b;
+      bp.dy_pool = dy_pool; bp.dy_scale = dy_pool_scale;
     } else {
       bp.y = R + rl.ylayer[l]; bp.y_st = (long long)d.B * d.DH; bp.y_sb = (long long)d.DH;
       bp.dy = S + sl.b_dy; bp.dy_st = (long long)d.B * d.DH; bp.dy_sb = (long long)d.DH;
@@ -525,14 +551,19 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
     // layer input as seen by the forward GEMM
     const float* in;
     RowMap in_rows;
-    if (l == 0) {
+    if (l == 0 && fused_ln) {  // what the forward GEMM multiplied: LayerNorm(x), saved densely by the prologue
+      in = R + rl.xln;
+      in_rows = simple_rows((long long)d.I);
+    } else if (l == 0) {
       in = x;
       in_rows = tb_rows(xs_t, xs_b, d.B);
     } else {
       in = R + (drop ? rl.ydrop[l - 1] : rl.ylayer[l - 1]);
       in_rows = simple_rows((long long)d.DH);
     }
-    const bool want_dx = (l > 0) || (dx != nullptr);
+    // with the fused LayerNorm the layer-0 dgrad is d/dLN(x): it goes to scratch and through the LN backward below
+    const bool ln_l0 = (l == 0) && fused_ln;
+    const bool want_dx = (l > 0) || (dx != nullptr) || (ln_l0 && (dln_gamma || dln_beta));
     // ---- tcgen05 3xTF32 path for the wgrad / dgrad GEMMs (falls back to the FFMA kernel per GEMM) -------------
     const long long ldk = sl.b_ldk;
     const bool tc_l = tc_available() && (Il % 128 == 0);
@@ -602,7 +633,9 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
         if (want_dx) {  // dX_l (+)= dGi[TB, GH] * W_ih[GH, Il]
           float* Cx;
           RowMap cx_rows;
-          if (l == 0) {
+          if (ln_l0) {
+            Cx = S + sl.b_dxln; cx_rows = simple_rows((long long)d.I);
+          } else if (l == 0) {
             Cx = dx; cx_rows = tb_rows(dxs_t, dxs_b, d.B);
           } else {
             Cx = S + sl.b_dy; cx_rows = simple_rows((long long)d.DH);
@@ -673,7 +706,9 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
         memset(&g, 0, sizeof(g));
         g.A = dG; g.a_rows = simple_rows((long long)d.GH); g.a_kcontig = 1;
         g.B = pp[0]; g.b_rows = simple_rows(Il); g.b_kcontig = 0;
-        if (l == 0) {
+        if (ln_l0) {
+          g.C = S + sl.b_dxln; g.c_rows = simple_rows((long long)d.I);
+        } else if (l == 0) {
           g.C = dx; g.c_rows = tb_rows(dxs_t, dxs_b, d.B);
         } else {
           g.C = S + sl.b_dy; g.c_rows = simple_rows((long long)d.DH);
@@ -688,8 +723,27 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
       rc = launch_dropout(S + sl.b_dy, S + sl.b_dy, d.TB * d.DH, d.p, hdr, (uint32_t)(l - 1), st);
       if (rc) return rc;
     }
+    if (ln_l0 && want_dx) {  // LayerNorm backward: dx (caller's layout), dgamma, dbeta
+      rc = launch_layernorm_bwd(x, tb_rows(xs_t, xs_b, d.B), S + sl.b_dxln, (int)d.TB, d.I, ln_gamma, ln_eps, dx,
+                                tb_rows(dxs_t, dxs_b, d.B), dln_gamma, dln_beta, accumulate, S + sl.b_lnpart, st);
+      if (rc) return rc;
+    }
   }
   return B200RNN_OK;
+}
+
+B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64_t xs_t, int64_t xs_b,
+                                 const float* const* params, const float* y, int64_t ys_t, int64_t ys_b,
+                                 const float* dy, int64_t dys_t, int64_t dys_b, const float* dh_n,
+                                 const float* dc_n, const void* reserve, void* scratch, float* dx, int64_t dxs_t,
+                                 int64_t dxs_b, float* const* dparams, const int32_t* lengths, void* stream_) {
+  if (!dy) {
+    set_error("backward: null pointer argument");
+    return B200RNN_ERR_INVALID;
+  }
+  return b200rnn_backward_fused(desc, x, xs_t, xs_b, params, y, ys_t, ys_b, dy, dys_t, dys_b, nullptr, 0.f, dh_n, dc_n,
+                                reserve, scratch, dx, dxs_t, dxs_b, dparams, lengths, nullptr, 0.f, nullptr, nullptr,
+                                stream_);
 }
 
 B200RNN_API int b200rnn_gemm_f32(int M, int N, int K, const float* A, int64_t lda, int a_kcontig, const float* B,

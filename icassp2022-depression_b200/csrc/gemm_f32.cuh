@@ -33,8 +33,15 @@ struct GemmParams {
 float* tc_a_hi(void* ws);
 float* tc_a_lo(void* ws, int M, int K);
 // LayerNorm over the last dimension fused with the TF32 split: hi/lo <- split(LN(src row) * gamma + beta)
+// `out` (optional): dense [R][Cc] copy of LN(src) kept for the backward pass (layer-0 wgrad operand)
 int tc_layernorm_split(const float* src, const RowMap& rows, int R, int Cc, const float* gamma, const float* beta,
-                       float eps, float* hi, float* lo, cudaStream_t stream);
+                       float eps, float* hi, float* lo, cudaStream_t stream, float* out = nullptr);
+// backward of that prologue: dx (strided like x) from dy = d/dLN(x) (dense), dgamma / dbeta (+)=; part = scratch of
+// layernorm_bwd_scratch_floats(Cc) floats
+size_t layernorm_bwd_scratch_floats(int Cc);
+int launch_layernorm_bwd(const float* x, const RowMap& x_rows, const float* dy, int R, int Cc, const float* gamma,
+                         float eps, float* dx, const RowMap& dx_rows, float* dgamma, float* dbeta, int accumulate,
+                         float* part, cudaStream_t stream);
 
 // tcgen05 3xTF32 path: C = A[M,K] * B[N,K]^T + biases (both operands k-contiguous, K % 32 == 0, N % 128 == 0)
 size_t gemm_tc_scratch_bytes(int M, int N, int K);

@@ -32,6 +32,7 @@ namespace b200rnn {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int LNB_BLOCKS = 148 * 2;  // CTAs of the LayerNorm backward (per-CTA column partials, reduced in fixed order)
 constexpr int TILE_BYTES = BM * BK * 4;        // 16 KB, both A and W tiles (BM == BN)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi, A_lo, W_hi, W_lo
 constexpr int TC_THREADS = 256;
@@ -322,7 +323,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, RowMap rows, in
 template <int NV>  // float4 per lane
 __global__ void layernorm_split_kernel(const float* __restrict__ src, RowMap rows, int R, int Cc,
                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                       float* __restrict__ hi, float* __restrict__ lo) {
+                                       float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += gridDim.x * wpb) {
@@ -363,7 +364,101 @@ __global__ void layernorm_split_kernel(const float* __restrict__ src, RowMap row
       }
       *reinterpret_cast<float4*>(hi + (size_t)r * Cc + k) = make_float4(h[0], h[1], h[2], h[3]);
       *reinterpret_cast<float4*>(lo + (size_t)r * Cc + k) = make_float4(l[0], l[1], l[2], l[3]);
+      if (out) *reinterpret_cast<float4*>(out + (size_t)r * Cc + k) = make_float4(y[0], y[1], y[2], y[3]);  // for backward
     }
+  }
+}
+
+// LayerNorm backward for the folded prologue: dy = gradient w.r.t. LN(x) (dense [R][Cc], produced by the layer-0 dgrad
+// GEMM), x read through the caller's row map, statistics recomputed (cheaper than saving them):
+//   xhat = (x - mean) rstd;  g = dy * gamma;  dx = rstd (g - mean(g) - xhat mean(g xhat))
+//   dgamma += sum_rows dy xhat;  dbeta += sum_rows dy      (per-CTA partials here, fixed-order reduce below)
+// One warp per row, each lane keeps the column partials of its 4*NV columns in registers across its rows.
+template <int NV>
+__global__ void layernorm_bwd_kernel(const float* __restrict__ x, RowMap x_rows, const float* __restrict__ dy, int R,
+                                     int Cc, const float* __restrict__ gamma, float eps, float* __restrict__ dx,
+                                     RowMap dx_rows, float* __restrict__ part /* [grid][2][Cc] */) {
+  extern __shared__ float red[];  // [warps][2][Cc]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  float4 dg[NV], db[NV], gm[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4));
+  }
+  for (int r = blockIdx.x * wpb + warp; r < R; r += gridDim.x * wpb) {
+    const float* px = x + x_rows.off(r);
+    const float* pd = dy + (size_t)r * Cc;
+    float4 xv[NV], dv[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      xv[i] = __ldg(reinterpret_cast<const float4*>(px + i * 128 + lane * 4));
+      dv[i] = *reinterpret_cast<const float4*>(pd + i * 128 + lane * 4);
+      s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)Cc;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
+      v += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v / (float)Cc + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;  // xhat
+      dg[i].x += dv[i].x * xv[i].x; dg[i].y += dv[i].y * xv[i].y; dg[i].z += dv[i].z * xv[i].z; dg[i].w += dv[i].w * xv[i].w;
+      db[i].x += dv[i].x; db[i].y += dv[i].y; db[i].z += dv[i].z; db[i].w += dv[i].w;
+      dv[i].x *= gm[i].x; dv[i].y *= gm[i].y; dv[i].z *= gm[i].z; dv[i].w *= gm[i].w;  // g = dy * gamma
+      sg += (dv[i].x + dv[i].y) + (dv[i].z + dv[i].w);
+      sgx += (dv[i].x * xv[i].x + dv[i].y * xv[i].y) + (dv[i].z * xv[i].z + dv[i].w * xv[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+    }
+    const float mg = sg / (float)Cc, mgx = sgx / (float)Cc;
+    if (dx) {
+      float* po = dx + dx_rows.off(r);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float4 o4;
+        o4.x = rstd * (dv[i].x - mg - xv[i].x * mgx);
+        o4.y = rstd * (dv[i].y - mg - xv[i].y * mgx);
+        o4.z = rstd * (dv[i].z - mg - xv[i].z * mgx);
+        o4.w = rstd * (dv[i].w - mg - xv[i].w * mgx);
+        *reinterpret_cast<float4*>(po + i * 128 + lane * 4) = o4;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    *reinterpret_cast<float4*>(red + ((size_t)warp * 2 + 0) * Cc + i * 128 + lane * 4) = dg[i];
+    *reinterpret_cast<float4*>(red + ((size_t)warp * 2 + 1) * Cc + i * 128 + lane * 4) = db[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * Cc; c += blockDim.x) {
+    float a = 0.f;
+    for (int w2 = 0; w2 < wpb; ++w2) a += red[(size_t)w2 * 2 * Cc + c];  // fixed order
+    part[(size_t)blockIdx.x * 2 * Cc + c] = a;
+  }
+}
+__global__ void layernorm_bwd_reduce_kernel(const float* __restrict__ part, int nparts, int Cc, float* __restrict__ dgamma,
+                                            float* __restrict__ dbeta, int accumulate) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < 2 * Cc; c += gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int p2 = 0; p2 < nparts; ++p2) a += part[(size_t)p2 * 2 * Cc + c];  // fixed order => deterministic
+    float* dst = c < Cc ? (dgamma ? dgamma + c : nullptr) : (dbeta ? dbeta + (c - Cc) : nullptr);
+    if (dst) *dst = accumulate ? *dst + a : a;
   }
 }
 
@@ -483,7 +578,7 @@ float* tc_a_hi(void* ws) { return reinterpret_cast<float*>((reinterpret_cast<uin
 float* tc_a_lo(void* ws, int M, int K) { return tc_a_hi(ws) + (size_t)M * K; }
 
 int tc_layernorm_split(const float* src, const RowMap& rows, int R, int Cc, const float* gamma, const float* beta,
-                       float eps, float* hi, float* lo, cudaStream_t stream) {
+                       float eps, float* hi, float* lo, cudaStream_t stream, float* out) {
   const bool vec = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && rows.s_outer % 4 == 0 && rows.s_inner % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15u) == 0;
   if (!vec || Cc % 128 != 0 || Cc > 1024 || Cc < 128) {
@@ -494,17 +589,54 @@ int tc_layernorm_split(const float* src, const RowMap& rows, int R, int Cc, cons
   if (blocks > 148 * 8) blocks = 148 * 8;
   ProfScope prof(PROF_MISC, stream);
   switch (Cc / 128) {
-    case 1: layernorm_split_kernel<1><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
-    case 2: layernorm_split_kernel<2><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
-    case 3: layernorm_split_kernel<3><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
-    case 4: layernorm_split_kernel<4><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
-    case 5: layernorm_split_kernel<5><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
-    case 6: layernorm_split_kernel<6><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
-    case 7: layernorm_split_kernel<7><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
-    default: layernorm_split_kernel<8><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo); break;
+    case 1: layernorm_split_kernel<1><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
+    case 2: layernorm_split_kernel<2><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
+    case 3: layernorm_split_kernel<3><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
+    case 4: layernorm_split_kernel<4><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
+    case 5: layernorm_split_kernel<5><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
+    case 6: layernorm_split_kernel<6><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
+    case 7: layernorm_split_kernel<7><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
+    default: layernorm_split_kernel<8><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
   }
   B200_CUDA_CHECK(cudaGetLastError());
   count_launch();
+  return B200RNN_OK;
+}
+
+size_t layernorm_bwd_scratch_floats(int Cc) { return (size_t)LNB_BLOCKS * 2 * Cc; }
+
+int launch_layernorm_bwd(const float* x, const RowMap& x_rows, const float* dy, int R, int Cc, const float* gamma,
+                         float eps, float* dx, const RowMap& dx_rows, float* dgamma, float* dbeta, int accumulate,
+                         float* part, cudaStream_t stream) {
+  const bool vec = (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && x_rows.s_outer % 4 == 0 && x_rows.s_inner % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15u) == 0 &&
+                   (!dx || ((reinterpret_cast<uintptr_t>(dx) & 15u) == 0 && dx_rows.s_outer % 4 == 0 &&
+                            dx_rows.s_inner % 4 == 0));
+  if (!vec || Cc % 128 != 0 || Cc > 1024 || Cc < 128) {
+    set_error("layernorm_bwd: needs 16-byte aligned rows and a feature width in {128,...,1024} multiple of 128");
+    return B200RNN_ERR_UNSUPPORTED;
+  }
+  int blocks = (R + 7) / 8;
+  if (blocks > LNB_BLOCKS) blocks = LNB_BLOCKS;
+  const size_t smem = (size_t)8 * 2 * Cc * sizeof(float);
+  ProfScope prof(PROF_MISC, stream);
+#define B200_LNB(NV_) \
+  layernorm_bwd_kernel<NV_><<<blocks, 256, smem, stream>>>(x, x_rows, dy, R, Cc, gamma, eps, dx, dx_rows, part)
+  switch (Cc / 128) {
+    case 1: B200_LNB(1); break;
+    case 2: B200_LNB(2); break;
+    case 3: B200_LNB(3); break;
+    case 4: B200_LNB(4); break;
+    case 5: B200_LNB(5); break;
+    case 6: B200_LNB(6); break;
+    case 7: B200_LNB(7); break;
+    default: B200_LNB(8); break;
+  }
+#undef B200_LNB
+  B200_CUDA_CHECK(cudaGetLastError());
+  layernorm_bwd_reduce_kernel<<<(2 * Cc + 255) / 256, 256, 0, stream>>>(part, blocks, Cc, dgamma, dbeta, accumulate);
+  B200_CUDA_CHECK(cudaGetLastError());
+  count_launch(2);
   return B200RNN_OK;
 }
 

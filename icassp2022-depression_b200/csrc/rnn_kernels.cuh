@@ -29,8 +29,10 @@ struct RecBwdParams {
   const float* extra[2];     // GRU hn / LSTM c, [T,B,H]
   const float* y;            // this layer's forward output (h_t), strided
   long long y_st, y_sb;
-  const float* dy;           // gradient of this layer's output, strided
+  const float* dy;           // gradient of this layer's output, strided (NULL: use dy_pool)
   long long dy_st, dy_sb;
+  const float* dy_pool;      // [B, D*H]: gradient of the time-POOLED output, broadcast over the steps inside the kernel
+  float dy_scale;            //           (x dy_scale): the [T,B,D*H] gradient of a mean / sum over time never exists
   const float* dh_n;         // [D,B,H] or NULL
   const float* dc_n;         // [D,B,H] or NULL
   float* dgates[2];          // out: [T,B,G*H] gradient w.r.t. the x-projection (dGi)

@@ -363,7 +363,9 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
   const float* w_prep = p.w_prep[dir] + (size_t)rank * G * HS * H;
 
   if (tid == 0) {
-    for (int i = 0; i < Cfg::NBAR; ++i) ptx::mbar_init(&bars[i], 1);
+    // as in the forward: the own slice is delivered locally (G gate-gradient slices x NW warps arrive per phase)
+    for (int i = 0; i < Cfg::NBAR; ++i)
+      ptx::mbar_init(&bars[i], (i >= 1 && (uint32_t)((i - 1) % C) == rank) ? (uint32_t)(Cfg::NW * G) : 1u);
     ptx::fence_mbar_init();
   }
   __syncthreads();
@@ -403,6 +405,8 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
 #pragma unroll
   for (int g = 0; g <= G; ++g) bsum[g] = 0.f;
 
+  // pooled output (mean / sum over time fused into the caller's graph): every step receives the same gradient row
+  const float dy_pooled = (!p.dy && p.dy_pool && valid) ? p.dy_pool[(size_t)b * p.D * H + dir * H + j] * p.dy_scale : 0.f;
   // operands of the current step (prefetched one step ahead)
   float sv[G], sx = 0.f, hp = 0.f, dyv = 0.f;  // saved gates, hn / c_t, h_{prev} / c_{prev}, dy
 #pragma unroll
@@ -415,7 +419,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
 #pragma unroll
     for (int g = 0; g < G; ++g) sv[g] = gp[g * H];
     sx = extra[((size_t)t * B + b) * H + j];
-    dyv = p.dy[(long long)t * p.dy_st + (long long)b * p.dy_sb + dir * H + j];
+    dyv = p.dy ? p.dy[(long long)t * p.dy_st + (long long)b * p.dy_sb + dir * H + j] : dy_pooled;
     if (MODE == B200RNN_GRU)
       hp = has_prev ? p.y[(long long)tp * p.y_st + (long long)b * p.y_sb + dir * H + j] : 0.f;
     else
@@ -431,7 +435,8 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     if (tid == 0 && !last) {
 #pragma unroll
       for (int src = 0; src < C; ++src)
-        ptx::mbar_arrive_expect_tx(&bars[1 + buf * C + src], (uint32_t)(BS * G * HS * sizeof(float)));
+        if ((uint32_t)src != rank)
+          ptx::mbar_arrive_expect_tx(&bars[1 + buf * C + src], (uint32_t)(BS * G * HS * sizeof(float)));
     }
 
     // ---- cell backward for (unit j, batch b) ----------------------------------------------------
@@ -487,7 +492,8 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
         float v = dg[g];
         if (MODE == B200RNN_GRU && g == 2) v = dhn;
         if (!valid) v = 0.f;
-        allgather_units<C, KL, UPL, BS>(v, d_buf, GH, g * H + j0 + w * UPW, &bars[1 + buf * C + rank], lane);
+        allgather_units<C, KL, UPL, BS, true>(v, d_buf, GH, g * H + j0 + w * UPW, &bars[1 + buf * C + rank], lane,
+                                              rank);
       }
     }
 

@@ -52,6 +52,9 @@ enum {
 /* flags */
 #define B200RNN_FLAG_ACCUMULATE_GRADS 1u  /* backward: dparams += grad (else dparams = grad)          */
 #define B200RNN_FLAG_SAVE_FOR_BACKWARD 2u /* forward: keep gates / cell state / layer outputs in `reserve` */
+#define B200RNN_FLAG_FUSED_LN 4u          /* the LayerNorm prologue is part of the differentiated graph: the forward keeps
+                                             LN(x) in `reserve`, b200rnn_backward_fused runs the LayerNorm backward.
+                                             Must be set identically for workspace_bytes / forward_fused / backward_fused */
 
 /*
  * Problem descriptor. Mirrors the constructor arguments of torch.nn.GRU / torch.nn.LSTM
@@ -167,6 +170,26 @@ B200RNN_API int b200rnn_backward(const b200rnn_desc* desc, const float* x, int64
                                  int64_t dy_stride_b, const float* dh_n, const float* dc_n, const void* reserve,
                                  void* scratch, float* dx, int64_t dx_stride_t, int64_t dx_stride_b,
                                  float* const* dparams, const int32_t* lengths, void* stream /* cudaStream_t */);
+
+/*
+ * Backward with the model-shell fusions of the TRAINING path (audio_gru_whole.py:103-108 with
+ * loss.backward() at :190): b200rnn_backward plus
+ *   dy_pool / dy_pool_scale : when dy == NULL the top layer's output gradient is dy_pool[b, c] * dy_pool_scale for
+ *                             EVERY time step - the gradient of `x.mean(dim=1)` / `x.sum(dim=1)` over the encoder output
+ *                             (audio_gru_whole.py:106, audio_bilstm_perm.py:125) broadcast inside the BPTT kernel, so the
+ *                             [T,B,D*H] gradient tensor is never written nor read
+ *   ln_gamma / ln_eps       : with B200RNN_FLAG_FUSED_LN: the layer-0 input gradient is d/dLN(x); it is pushed through
+ *                             the LayerNorm backward (statistics recomputed from x) into dx, and
+ *   dln_gamma / dln_beta    : (+)= the LayerNorm parameter gradients (NULL to skip), per B200RNN_FLAG_ACCUMULATE_GRADS
+ */
+B200RNN_API int b200rnn_backward_fused(const b200rnn_desc* desc, const float* x, int64_t x_stride_t,
+                                       int64_t x_stride_b, const float* const* params, const float* y,
+                                       int64_t y_stride_t, int64_t y_stride_b, const float* dy, int64_t dy_stride_t,
+                                       int64_t dy_stride_b, const float* dy_pool, float dy_pool_scale,
+                                       const float* dh_n, const float* dc_n, const void* reserve, void* scratch,
+                                       float* dx, int64_t dx_stride_t, int64_t dx_stride_b, float* const* dparams,
+                                       const int32_t* lengths, const float* ln_gamma, float ln_eps, float* dln_gamma,
+                                       float* dln_beta, void* stream /* cudaStream_t */);
 
 /*
  * Dense helper used by the path (time-parallel input projection, wgrad, dgrad):

@@ -213,3 +213,42 @@ def test_frozen_weight_cache_is_bitwise_neutral_and_follows_weight_updates():
         assert gru.frozen_weight_cache() is None
         assert torch.equal(gru.forward_ln_sum(x, ln), got)  # uncached result with the edited weights
         assert not torch.equal(got, base)
+
+
+@pytest.mark.parametrize("B,T,reg", [(64, 120, False), (5, 7, False), (6, 9, True)])
+def test_fused_ln_gru_pool_under_autograd_matches_cpu_oracle(B, T, reg):
+    """SURVEY.md 8f rank 1 for the TRAINING path (audio_gru_whole.py:103-108 + loss.backward() :190): LayerNorm folded
+    into the layer-0 projection forward and backward, time pooling in the recurrence epilogue, pooled gradient
+    broadcast inside the BPTT kernel - against oracle.ref_models.RefAudio (stock torch, CPU) at BASELINE c2 size."""
+    import b200rnn
+    from oracle import ref_models
+
+    torch.manual_seed(1)
+    cfg = dict(num_classes=1 if reg else 2, dropout=0.0, rnn_layers=2, embedding_size=256, hidden_dims=256)
+    ref = ref_models.RefAudio(cfg, regression=reg).train()
+    mine = b200rnn.AudioBiLSTM(cfg, regression=reg)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(DEV).train()
+    x = torch.randn(B, T, 256)
+    w = torch.randn(B, cfg["num_classes"])
+    xr = x.clone().requires_grad_(True)
+    xm = x.clone().to(DEV).requires_grad_(True)
+    out_r = ref(xr)
+    (out_r * w).sum().backward()
+    out_m = mine(xm)
+    (out_m * w.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    assert (out_m.cpu() - out_r.detach()).abs().max().item() < 1e-4 * max(1.0, out_r.abs().max().item())
+    gx = xr.grad
+    assert (xm.grad.cpu() - gx).abs().max().item() <= 1e-4 * gx.abs().max().item()
+    ref_g = dict(ref.named_parameters())
+    gmax = max(p.grad.abs().max().item() for p in ref.parameters() if p.grad is not None)
+    n = 0
+    for name, p in mine.named_parameters():
+        if ref_g[name].grad is None:
+            continue
+        assert p.grad is not None, name
+        err = (p.grad.cpu() - ref_g[name].grad).abs().max().item()
+        assert err <= 1e-4 * gmax, (name, err, gmax)
+        n += 1
+    assert n >= (14 if not reg else 12)

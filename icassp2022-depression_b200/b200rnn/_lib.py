@@ -34,6 +34,7 @@ SYMBOLS = (
     "b200rnn_prepare_weights",
     "b200rnn_gemm_f32",
     "b200rnn_attention_pool",
+    "b200rnn_attention_pool_bwd",
     "b200rnn_mlp_dropout",
     "b200rnn_rng_next",
     "b200rnn_fuse_loss_grad",
@@ -189,6 +190,10 @@ def load() -> ctypes.CDLL:
     lib.b200rnn_attention_pool.restype = c_int
     lib.b200rnn_attention_pool.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                            c_void_p, c_void_p, c_void_p]
+    lib.b200rnn_attention_pool_bwd.restype = c_int
+    lib.b200rnn_attention_pool_bwd.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                                               c_void_p, c_void_p]
     lib.b200rnn_mlp_dropout.restype = c_int
     lib.b200rnn_mlp_dropout.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
                                         c_uint32, c_void_p]

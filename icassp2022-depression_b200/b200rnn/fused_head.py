@@ -50,6 +50,69 @@ def attention_pool(seq_tm: torch.Tensor, h_n: torch.Tensor, attention_layer: tor
     return ctx
 
 
+class _AttentionPoolFunction(torch.autograd.Function):
+    """ctx[B,H] = attention_net_with_w(seq, h_n) as ONE kernel forward and ONE kernel backward (plus the [H,B]x[B,H]
+    weight-gradient product): ``b200rnn_attention_pool`` / ``b200rnn_attention_pool_bwd``."""
+
+    @staticmethod
+    def forward(ctx, seq_tm: torch.Tensor, h_n: torch.Tensor, w: torch.Tensor, b: torch.Tensor):
+        lib = _lib.load()
+        T, B, H2 = seq_tm.shape
+        H = H2 // 2
+        if seq_tm.stride(2) != 1:
+            seq_tm = seq_tm.contiguous()
+        h_n = h_n.contiguous()
+        out = torch.empty(B, H, dtype=torch.float32, device=seq_tm.device)
+        with _on(seq_tm.device):
+            rc = lib.b200rnn_attention_pool(seq_tm.data_ptr(), seq_tm.stride(0), seq_tm.stride(1), h_n.data_ptr(),
+                                            h_n.shape[0], B, T, H, w.data_ptr(), b.data_ptr(), out.data_ptr(),
+                                            _stream(seq_tm.device))
+        _lib.check(rc, "b200rnn_attention_pool")
+        ctx.save_for_backward(seq_tm, h_n, w, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, dctx):
+        from .functional import gemm
+
+        lib = _lib.load()
+        seq_tm, h_n, w, b = ctx.saved_tensors
+        T, B, H2 = seq_tm.shape
+        H = H2 // 2
+        dev = seq_tm.device
+        dctx = dctx.contiguous()
+        dseq = torch.empty(T, B, H2, dtype=torch.float32, device=dev)
+        dh_n = torch.empty_like(h_n)
+        dqpre = torch.empty(B, H, dtype=torch.float32, device=dev)
+        hsum = torch.empty(B, H, dtype=torch.float32, device=dev)
+        with _on(dev):
+            rc = lib.b200rnn_attention_pool_bwd(seq_tm.data_ptr(), seq_tm.stride(0), seq_tm.stride(1), h_n.data_ptr(),
+                                                h_n.shape[0], B, T, H, w.data_ptr(), b.data_ptr(), dctx.data_ptr(),
+                                                dseq.data_ptr(), dseq.stride(0), dseq.stride(1), dh_n.data_ptr(),
+                                                dqpre.data_ptr(), hsum.data_ptr(), _stream(dev))
+        _lib.check(rc, "b200rnn_attention_pool_bwd")
+        dw = db = None
+        if ctx.needs_input_grad[2]:     # dW[i,j] = sum_b dqpre[b,i] hsum[b,j]: A = dqpre as [K=B, M=H], B = hsum as [K=B, N=H]
+            dw = gemm(dqpre, hsum, a_kcontig=False, b_kcontig=False, use_splitk=False)
+        if ctx.needs_input_grad[3]:
+            db = dqpre.sum(dim=0)
+        return dseq, dh_n, dw, db
+
+
+def attention_pool_tm(attention_layer: torch.nn.Module, seq_tm: torch.Tensor, h_n: torch.Tensor) -> torch.Tensor:
+    """``attention_net_with_w`` (text_bilstm_whole.py:74-99) on the TIME-MAJOR LSTM output ``seq_tm`` [T,B,2H] and
+    ``h_n`` [L*D,B,H] -> [B,H]; differentiable (one kernel each way). Falls back to the PyTorch expression only for
+    shapes the kernels do not take (T*H beyond one CTA's shared memory) or non-CUDA tensors of the oracle tests."""
+    lin = attention_layer[0]
+    T, B, H2 = seq_tm.shape
+    fits = (4 * (H2 // 2) + 2 * T + T * (H2 // 2)) * 4 <= 200 * 1024 and (2 * (H2 // 2) + T) * 4 <= 48 * 1024
+    if seq_tm.is_cuda and fits and seq_tm.dtype == torch.float32:
+        return _AttentionPoolFunction.apply(seq_tm, h_n, lin.weight, lin.bias)
+    from .models import attention_pool as _generic
+
+    return _generic(attention_layer, seq_tm.permute(1, 0, 2), h_n.permute(1, 0, 2))
+
+
 @torch.no_grad()
 def mlp_dropout(x: torch.Tensor, linear: torch.nn.Linear, p: float, training: bool, rng_hdr: Optional[torch.Tensor],
                 stream_id: int) -> torch.Tensor:

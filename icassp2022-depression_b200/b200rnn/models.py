@@ -139,7 +139,9 @@ class TextBiLSTM(nn.Module):
     def context(self, x: torch.Tensor) -> torch.Tensor:
         # [B,T,E] -> time-major NON-contiguous view, consumed in place by the kernels (text_bilstm_whole.py:103)
         seq, (h_n, _) = self.lstm_net(x.permute(1, 0, 2))
-        return attention_pool(self.attention_layer, seq.permute(1, 0, 2), h_n.permute(1, 0, 2))
+        from .fused_head import attention_pool_tm   # one kernel forward, one backward
+
+        return attention_pool_tm(self.attention_layer, seq, h_n)
 
     def forward_logits(self, x: torch.Tensor) -> torch.Tensor:
         """``forward`` without the final activation (see AudioBiLSTM.forward_logits)."""
@@ -191,9 +193,10 @@ class fusion_net(nn.Module):  # noqa: N801  (reference class name)
         """
         with torch.no_grad():
             batch = x if isinstance(x, FuseBatch) else stage_fuse_batch(x, self.fc_final[0].weight.device)
+            from .fused_head import attention_pool_tm
+
             seq, (h_n, _) = self.lstm_net(batch.text.permute(1, 0, 2))
-            ctx = attention_pool(self.attention_layer, seq.permute(1, 0, 2), h_n.permute(1, 0, 2))
-            text_feature = self.fc_out(ctx)
+            text_feature = self.fc_out(attention_pool_tm(self.attention_layer, seq, h_n))
 
             # LayerNorm (classification flavour only) -> GRU -> sum over time, fused around the encoder
             pooled = self.lstm_net_audio.forward_ln_sum(batch.audio, None if self.regression else self.ln)

@@ -166,12 +166,12 @@ class FuseFineTuneStep(TrainStep):
         self.criterion = criterion or MyLoss(model.text_hidden_dims, regression=model.regression)
 
     def _body(self):
-        from .models import attention_pool
+        from .fused_head import attention_pool_tm
 
         m = self.model
         self.opt.zero_grad()
         seq, (h_n, _) = m.lstm_net(self.text.permute(1, 0, 2))
-        tf = m.fc_out(attention_pool(m.attention_layer, seq.permute(1, 0, 2), h_n.permute(1, 0, 2)))
+        tf = m.fc_out(attention_pool_tm(m.attention_layer, seq, h_n))
         af = m.fc_audio(m.lstm_net_audio.forward_ln_sum(self.x, None if m.regression else m.ln))
         out = m(torch.cat((tf, af), dim=1))
         loss = self.criterion(tf, af, self.y, m)

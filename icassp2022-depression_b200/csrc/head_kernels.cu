@@ -94,6 +94,110 @@ __global__ void attention_pool_kernel(const float* __restrict__ seq, long long s
   }
 }
 
+// ---- backward of the attention pooling (text_bilstm_whole.py:74-99 under loss.backward()): one CTA per batch row ------
+//   forward (recomputed): hsum = sum_k h_n[k,b]; qpre = W hsum + b; q = ReLU(qpre); h_t = seq[t,b,:H] + seq[t,b,H:];
+//                         s_t = q . tanh(h_t); a = softmax_t(s); ctx = sum_t a_t h_t
+//   backward: da_t = dctx . h_t; ds_t = a_t (da_t - sum_u a_u da_u); dq = sum_t ds_t tanh(h_t);
+//             dh_t = a_t dctx + ds_t q (1 - tanh(h_t)^2)  -> both halves of dseq[t,b,:]
+//             dqpre = dq [qpre > 0]; dhsum = W^T dqpre -> every dh_n[k,b,:];  dW = sum_b dqpre hsum^T, db = sum_b dqpre
+//   (the two batch reductions are left to the caller: dqpre / hsum rows go to [B,H] buffers, dW is one small GEMM)
+__global__ void __launch_bounds__(256)
+    attention_pool_bwd_kernel(const float* __restrict__ seq, long long s_t, long long s_b, const float* __restrict__ h_n,
+                              int NS, int B, int T, int H, const float* __restrict__ w_a, const float* __restrict__ b_a,
+                              const float* __restrict__ dctx, float* __restrict__ dseq, long long d_t, long long d_b,
+                              float* __restrict__ dh_n, float* __restrict__ dqpre_out, float* __restrict__ hsum_out) {
+  extern __shared__ float sm[];
+  float* hsum = sm;            // [H]
+  float* qpre = hsum + H;      // [H]
+  float* dc = qpre + H;        // [H] dctx row
+  float* dqp = dc + H;         // [H]
+  float* score = dqp + H;      // [T] -> a_t
+  float* ds = score + T;       // [T]
+  float* hs = ds + T;          // [T][H] h_t
+  __shared__ float red[2];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const float* row0 = seq + (long long)b * s_b;
+  for (int j = tid; j < H; j += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < NS; ++k) s += h_n[((size_t)k * B + b) * H + j];
+    hsum[j] = s;
+    dc[j] = dctx[(size_t)b * H + j];
+    if (hsum_out) hsum_out[(size_t)b * H + j] = s;
+  }
+  for (int idx = tid; idx < T * H; idx += blockDim.x) {
+    const int t = idx / H, j = idx - t * H;
+    const float* r = row0 + (long long)t * s_t;
+    hs[idx] = r[j] + r[H + j];
+  }
+  __syncthreads();
+  for (int i = warp; i < H; i += nw) {  // qpre = W hsum + b
+    float s = 0.f;
+    for (int j = lane; j < H; j += 32) s += w_a[(size_t)i * H + j] * hsum[j];
+    s = warp_sum(s);
+    if (lane == 0) qpre[i] = s + b_a[i];
+  }
+  __syncthreads();
+  for (int t = warp; t < T; t += nw) {  // scores and da_t, one warp per time step
+    float s = 0.f, da = 0.f;
+    for (int j = lane; j < H; j += 32) {
+      const float h = hs[t * H + j];
+      s += fmaxf(qpre[j], 0.f) * tanhf(h);
+      da += dc[j] * h;
+    }
+    s = warp_sum(s);
+    da = warp_sum(da);
+    if (lane == 0) {
+      score[t] = s;
+      ds[t] = da;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {  // softmax over T, then ds_t = a_t (da_t - sum_u a_u da_u)
+    float m = -INFINITY;
+    for (int t = lane; t < T; t += 32) m = fmaxf(m, score[t]);
+    m = warp_max(m);
+    float z = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const float e = expf(score[t] - m);
+      score[t] = e;
+      z += e;
+    }
+    z = warp_sum(z);
+    const float inv = 1.f / z;
+    float dot = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const float a = score[t] * inv;
+      score[t] = a;
+      dot += a * ds[t];
+    }
+    dot = warp_sum(dot);
+    for (int t = lane; t < T; t += 32) ds[t] = score[t] * (ds[t] - dot);
+  }
+  __syncthreads();
+  for (int j = tid; j < H; j += blockDim.x) {
+    const float q = fmaxf(qpre[j], 0.f), dcj = dc[j];
+    float dq = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float th = tanhf(hs[t * H + j]);
+      dq += ds[t] * th;
+      const float dh = score[t] * dcj + ds[t] * q * (1.f - th * th);
+      float* o = dseq + (long long)t * d_t + (long long)b * d_b;
+      o[j] = dh;
+      o[H + j] = dh;
+    }
+    const float v = qpre[j] > 0.f ? dq : 0.f;
+    dqp[j] = v;
+    if (dqpre_out) dqpre_out[(size_t)b * H + j] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < H; i += blockDim.x) {  // dhsum = W^T dqpre (coalesced over i)
+    float s = 0.f;
+    for (int j = 0; j < H; ++j) s += w_a[(size_t)j * H + i] * dqp[j];
+    for (int k = 0; k < NS; ++k) dh_n[((size_t)k * B + b) * H + i] = s;
+  }
+  (void)red;
+}
+
 // ---- out = D2(ReLU(W D1(x) + bias)) as a small tiled GEMM: CTA tile = 32 outputs x 32 batch rows ---------------
 // Both operand tiles are staged in shared memory with bulk coalesced loads (no dependent global-load chains; the
 // first version, one warp-dot per output, spent its time waiting on one L2 round trip per 32 columns).
@@ -323,6 +427,32 @@ B200RNN_API int b200rnn_attention_pool(const float* seq, int64_t s_t, int64_t s_
   }
   attention_pool_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream_)>>>(seq, s_t, s_b, h_n, n_states, B, T, H, w_a,
                                                                              b_a, ctx);
+  B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return B200RNN_OK;
+}
+
+B200RNN_API int b200rnn_attention_pool_bwd(const float* seq, int64_t s_t, int64_t s_b, const float* h_n, int n_states,
+                                           int B, int T, int H, const float* w_a, const float* b_a, const float* dctx,
+                                           float* dseq, int64_t d_t, int64_t d_b, float* dh_n, float* dqpre,
+                                           float* hsum, void* stream_) {
+  if (!seq || !h_n || !w_a || !b_a || !dctx || !dseq || !dh_n || B < 0 || T < 1 || H < 1 || n_states < 1) {
+    set_error("attention_pool_bwd: bad argument");
+    return B200RNN_ERR_INVALID;
+  }
+  if (B == 0) return B200RNN_OK;
+  const size_t smem = ((size_t)4 * H + 2 * T + (size_t)T * H) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("attention_pool_bwd: T*H = %d floats exceed the shared-memory budget of one CTA", T * H);
+    return B200RNN_ERR_UNSUPPORTED;
+  }
+  static bool attr[MAX_DEVICES] = {false};
+  if (!attr[current_device()]) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(attention_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr[current_device()] = true;
+  }
+  attention_pool_bwd_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream_)>>>(seq, s_t, s_b, h_n, n_states, B, T, H, w_a,
+                                                                                 b_a, dctx, dseq, d_t, d_b, dh_n, dqpre, hsum);
   B200_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return B200RNN_OK;

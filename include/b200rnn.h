@@ -219,6 +219,14 @@ B200RNN_API int b200rnn_gemm_f32(int M, int N, int K, const float* A, int64_t ld
 B200RNN_API int b200rnn_attention_pool(const float* seq, int64_t s_t, int64_t s_b, const float* h_n, int n_states,
                                        int B, int T, int H, const float* w_a, const float* b_a, float* ctx,
                                        void* stream);
+/* Backward of b200rnn_attention_pool (the text models train through it: text_bilstm_whole.py:74-99, 182): one launch
+ * recomputes the forward per batch row and writes dseq [T,B,2H] (both halves), dh_n [n_states,B,H], and the two [B,H]
+ * row buffers dqpre / hsum from which the caller forms d attention_layer.0.weight = dqpre^T hsum (one small GEMM) and
+ * d attention_layer.0.bias = column sums of dqpre. */
+B200RNN_API int b200rnn_attention_pool_bwd(const float* seq, int64_t s_t, int64_t s_b, const float* h_n, int n_states,
+                                           int B, int T, int H, const float* w_a, const float* b_a, const float* dctx,
+                                           float* dseq, int64_t d_t, int64_t d_b, float* dh_n, float* dqpre,
+                                           float* hsum, void* stream);
 B200RNN_API int b200rnn_mlp_dropout(const float* x, int B, int n, const float* W, const float* bias, float* out,
                                     int training, float p, const uint64_t* rng_hdr, uint32_t stream_id, void* stream);
 B200RNN_API int b200rnn_rng_next(uint64_t* rng_hdr, uint64_t* rng_state, uint64_t consume, void* stream);

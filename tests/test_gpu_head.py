@@ -271,3 +271,28 @@ def test_fused_fuse_step_rejects_bad_labels():
     assert torch.isfinite(loss)
     _, loss = step(batch, torch.tensor([0, 1, 2, 0], device=DEV))                      # class 2 does not exist
     assert torch.isnan(loss)
+
+
+@pytest.mark.parametrize("T,B,H", [(30, 64, 256), (6, 5, 128), (1, 3, 128)])
+def test_attention_pool_autograd_function_matches_torch(T, B, H):
+    """b200rnn_attention_pool / _bwd as one autograd Function vs the PyTorch expression of text_bilstm_whole.py:74-99:
+    context, d seq (both halves), d h_n, d attention_layer weight and bias."""
+    import b200rnn
+    from b200rnn import fused_head
+
+    torch.manual_seed(21)
+    layer = torch.nn.Sequential(torch.nn.Linear(H, H), torch.nn.ReLU(inplace=True)).to(DEV)
+    seq = (torch.randn(T, B, 2 * H, device=DEV) * 0.5).requires_grad_(True)
+    h_n = (torch.randn(4, B, H, device=DEV) * 0.5).requires_grad_(True)
+    w = torch.randn(B, H, device=DEV)
+    got = fused_head.attention_pool_tm(layer, seq, h_n)
+    (got * w).sum().backward()
+    g1 = [seq.grad.clone(), h_n.grad.clone(), layer[0].weight.grad.clone(), layer[0].bias.grad.clone()]
+    for t in (seq, h_n, layer[0].weight, layer[0].bias):
+        t.grad = None
+    ref = b200rnn.attention_pool(layer, seq.permute(1, 0, 2), h_n.permute(1, 0, 2))
+    (ref * w).sum().backward()
+    g2 = [seq.grad, h_n.grad, layer[0].weight.grad, layer[0].bias.grad]
+    assert (got - ref).abs().max().item() < 1e-5
+    for a, b, name in zip(g1, g2, ("dseq", "dh_n", "dW", "db")):
+        assert (a - b).abs().max().item() <= 2e-5 * max(1.0, b.abs().max().item()), name

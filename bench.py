@@ -484,7 +484,7 @@ def run_ours(args) -> None:
     else:                   # the same step on the library's fused head kernel (b200rnn.FusedFuseStep): the gradient
         #                     exchange across ranks happens inside that kernel over NVLink peer stores ("peer") or,
         #                     with --exchange nccl, as a separate ncclAllReduce + Adam launch
-        fused = b200rnn.FusedFuseStep(model, lr=LR, exchange=args.exchange)
+        fused = b200rnn.FusedFuseStep(model, lr=LR, exchange=args.exchange, concurrent_branches=not args.one_stream)
         _log(f"rank {rank}: gradient exchange = {fused.exchange}")
 
     # ---- synthetic shards: rank r owns its own 128 sequences of the global batch (weak scaling) -------
@@ -659,6 +659,8 @@ def run_ours(args) -> None:
         "dtype": "f32", "data": "synthetic", "config": _config(n_gpus),
         "cuda_graph": bool(use_graph),
         "shells": "fused head kernel (b200rnn.FusedFuseStep)" if fused is not None else "PyTorch ops",
+        "encoder_branches": ("two streams (audio high priority)" if (fused is not None and fused.concurrent_branches)
+                             else "one stream"),
         "grad_exchange": (fused.exchange if fused is not None else ("nccl" if world > 1 else "none")),
         "gpu_launches": int(launches_per_step * K),
         "gpu_launches_per_step": int(launches_per_step),
@@ -833,6 +835,9 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing parity check against the CPU oracle")
     ap.add_argument("--quick", action="store_true", help="skip the secondary module timings")
+    ap.add_argument("--one-stream", action="store_true",
+                    help="serialise the audio and text encoder branches on one stream (default: the audio branch runs "
+                         "on a second, high-priority stream = parallel branches of the CUDA graph)")
     ap.add_argument("--exchange", choices=["auto", "peer", "nccl"], default="auto",
                     help="data-parallel gradient exchange of the fused step: in-kernel NVLink peer stores or NCCL")
     args = ap.parse_args()

@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_f
   float* score = gate + R * F;      // [R][Tpad]
   const int Tpad = (T + 3) & ~3;
   float* red = score + R * Tpad;    // [32] scratch
+  float* hst = red + 32;            // [R][T][Ht] h_t = fwd + rev halves of the BiLSTM output
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = HEAD_THREADS / 32;
   const int b0 = blockIdx.x * R;
@@ -152,15 +153,23 @@ __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_f
       hsum[idx] = s;
     }
     __syncthreads();
+    // h_t = seq[t,b,:Ht] + seq[t,b,Ht:] of this CTA's rows -> shared memory in ONE pass of independent, coalesced
+    // loads (the scores and the context both walk over t: from global memory that was ~2T dependent round trips)
+    for (int idx = tid; idx < R * T * Ht; idx += HEAD_THREADS) {
+      const int r = idx / (T * Ht), rem = idx - r * (T * Ht), t = rem / Ht, j = rem - t * Ht, b = b0 + r;
+      float v = 0.f;
+      if (b < B) {
+        const float* row = a.seq + (long long)t * a.seq_st + (long long)b * a.seq_sb;
+        v = row[j] + row[Ht + j];
+      }
+      hst[idx] = v;
+    }
     matvec_rows<R, true>(a.w_att, a.b_att, hsum, Ht, q, Ht, Ht, Ht, warp, nw, lane);  // q = ReLU(W_a hsum + b_a)
     __syncthreads();
     for (int idx = warp; idx < R * T; idx += nw) {  // scores: one warp per (row, time step)
-      const int r = idx / T, t = idx - r * T, b = b0 + r;
+      const int r = idx / T, t = idx - r * T;
       float s = 0.f;
-      if (b < B) {
-        const float* row = a.seq + (long long)t * a.seq_st + (long long)b * a.seq_sb;
-        for (int j = lane; j < Ht; j += 32) s += q[r * Ht + j] * tanhf(row[j] + row[Ht + j]);
-      }
+      for (int j = lane; j < Ht; j += 32) s += q[r * Ht + j] * tanhf(hst[(r * T + t) * Ht + j]);
       s = warp_sum(s);
       if (lane == 0) score[r * Tpad + t] = s;
     }
@@ -184,11 +193,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_f
       const int r = idx / Ht, j = idx - r * Ht, b = b0 + r;
       float acc = 0.f;
       if (b < B) {
-        const float* row0 = a.seq + (long long)b * a.seq_sb;
-        for (int t = 0; t < T; ++t) {
-          const float* row = row0 + (long long)t * a.seq_st;
-          acc += score[r * Tpad + t] * (row[j] + row[Ht + j]);
-        }
+        for (int t = 0; t < T; ++t) acc += score[r * Tpad + t] * hst[(r * T + t) * Ht + j];
         acc *= red[r];
         if (a.ctx_out) a.ctx_out[(size_t)b * Ht + j] = acc;
         if (drop) acc *= keep_scale(seed, offset, 0, (size_t)b * Ht + j, thr, scale);  // fc_out[0] Dropout
@@ -322,12 +327,12 @@ __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_f
     float g0 = 0.f, g1 = 0.f;
     const int so = (j < Ht) ? 0 : 2;
     int b = 0;
-    for (; b + 8 <= B; b += 8) {
-      float fv[8];
+    for (; b + 16 <= B; b += 16) {  // 16 independent coalesced loads in flight per thread, then the ordered adds
+      float fv[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) fv[u] = __ldcg(feat_ws + (size_t)(b + u) * F + j);
+      for (int u = 0; u < 16; ++u) fv[u] = __ldcg(feat_ws + (size_t)(b + u) * F + j);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 16; ++u) {
         g0 = fmaf(rst[(b + u) * ROWSTAT + so], fv[u], g0);
         g1 = fmaf(rst[(b + u) * ROWSTAT + so + 1], fv[u], g1);
       }
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_f
 
 size_t head_smem_floats(int B, int Ht, int Ha, int T, bool loss_stage) {
   const int F = Ht + Ha, Tpad = (T + 3) & ~3;
-  size_t n = (size_t)HEAD_ROWS * (3 * Ht + 2 * F + Ha + Tpad) + 32;
+  size_t n = (size_t)HEAD_ROWS * (3 * Ht + 2 * F + Ha + Tpad + (size_t)T * Ht) + 32;
   const size_t rst = loss_stage ? (size_t)B * ROWSTAT : 0;  // the last CTA re-uses the area for the per-row scalars
   return n > rst ? n : rst;
 }

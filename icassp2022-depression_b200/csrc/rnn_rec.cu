@@ -208,10 +208,10 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     long long* trow = p.trace + ((size_t)step * 8 + (w & 7)) * 8;
     if (tr) trow[0] = clock64();
 
-    // FFMA2 (two fp32 FMAs per issue slot; scalar FFMA retires one per two cycles and SMSP) wherever the packed
-    // accumulators fit the register file: the GRU (3 gates) and the LSTM with H = 128 (4 gates, but only 32 resident
-    // weight registers)
-    constexpr bool PACK2 = ((MODE == B200RNN_GRU) || H == 128) && RG < 2;
+    // FFMA2 (two fp32 FMAs per issue slot) for the GRU only. Measured on the LSTM H=128 forward (same box, round 2):
+    // FFMA2 53.6 us vs scalar FFMA 49.5 us per layer - with three distinct 64-bit register operands an FFMA2 issues
+    // every 3 cycles (register-file bandwidth), and the 4-gate packed accumulators leave the scheduler less room
+    constexpr bool PACK2 = (MODE == B200RNN_GRU) && RG < 2;
     float2 acc2[PACK2 ? G : 1][UPL][BS];
     float acc[G][UPL][BS];
 #pragma unroll

@@ -463,6 +463,9 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     torch.set_num_threads(1)   # the timed loops are launch loops: no intra-op pool spinning beside them (see top)
+    # pin the rank to the CPUs / memory of its GPU's NUMA node before any pinned buffer exists (8 ranks on a 2-socket box:
+    # 0.813 -> 0.773 ms/step device-resident, 0.877 -> 0.808 ms/step end-to-end)
+    numa = b200rnn.bind_host_thread_to_gpu_numa_node(dev)
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     n_gpus = world
@@ -485,7 +488,7 @@ def run_ours(args) -> None:
         #                     exchange across ranks happens inside that kernel over NVLink peer stores ("peer") or,
         #                     with --exchange nccl, as a separate ncclAllReduce + Adam launch
         fused = b200rnn.FusedFuseStep(model, lr=LR, exchange=args.exchange, concurrent_branches=not args.one_stream)
-        _log(f"rank {rank}: gradient exchange = {fused.exchange}")
+        _log(f"rank {rank}: gradient exchange = {fused.exchange}; numa binding {numa}")
 
     # ---- synthetic shards: rank r owns its own 128 sequences of the global batch (weak scaling) -------
     host = [_synthetic(B_PER_GPU, 1234 + 100 * rank + i) for i in range(N_ROTATE)]
@@ -661,6 +664,7 @@ def run_ours(args) -> None:
         "shells": "fused head kernel (b200rnn.FusedFuseStep)" if fused is not None else "PyTorch ops",
         "encoder_branches": ("two streams (audio high priority)" if (fused is not None and fused.concurrent_branches)
                              else "one stream"),
+        "numa_binding": numa,
         "grad_exchange": (fused.exchange if fused is not None else ("nccl" if world > 1 else "none")),
         "gpu_launches": int(launches_per_step * K),
         "gpu_launches_per_step": int(launches_per_step),
@@ -705,14 +709,15 @@ def run_ours(args) -> None:
         achieved = alg_bytes / t_launch / 1e9
         traffic = None   # dram bytes per launch from the committed ncu --set full capture of this kernel
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
-                traffic = json.load(fh)["r01_ncu_rec_fwd.csv"]["dram_bytes_per_launch"]
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as fh:
+                traffic = json.load(fh)["r02_ncu_rec_fwd.csv"]["dram_bytes_per_launch"]
         except Exception:
             pass
         line["roofline"] = {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": traffic, "traffic_source": "profiles/r01_ncu_rec_fwd.csv (ncu --set full, cold L2: includes the "
-                                                  "x-projection read that is an L2 hit in the real step)",
+            "traffic": traffic, "traffic_source": "profiles/r02_ncu_rec_fwd.csv (one ncu --set full capture of this kernel, "
+                                                  "cold L2: includes the x-projection read that is an L2 hit in the real "
+                                                  "step; a constant from that capture, not measured by this run)",
             "peak_source": peak_src,
             "kernel": "rec_fwd_kernel<GRU,H=256> (persistent cluster recurrence, one launch per layer)",
             "launch_ms": t_launch * 1e3, "launches_timed": rec_n,
@@ -838,7 +843,7 @@ def main() -> None:
     ap.add_argument("--one-stream", action="store_true",
                     help="serialise the audio and text encoder branches on one stream (default: the audio branch runs "
                          "on a second, high-priority stream = parallel branches of the CUDA graph)")
-    ap.add_argument("--exchange", choices=["auto", "peer", "nccl"], default="auto",
+    ap.add_argument("--exchange", choices=["auto", "peer", "nccl", "none"], default="auto",
                     help="data-parallel gradient exchange of the fused step: in-kernel NVLink peer stores or NCCL")
     args = ap.parse_args()
     _protect_stdout()

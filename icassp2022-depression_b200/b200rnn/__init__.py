@@ -8,7 +8,7 @@ from . import _lib
 from ._lib import B200RNNError
 from .modules import GRU, LSTM, from_torch, install, uninstall
 from .functional import RNNConfig, gemm, rnn_forward
-from .staging import FuseBatch, PinnedStager, stage_fuse_batch
+from .staging import FuseBatch, PinnedStager, bind_host_thread_to_gpu_numa_node, stage_fuse_batch
 from .dp import GradBucket, broadcast_parameters, shard_batch
 from .models import AudioBiLSTM, MyLoss, TextBiLSTM, attention_pool, fusion_net
 from .fused_head import FusedFuseStep

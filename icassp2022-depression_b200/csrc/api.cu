@@ -495,8 +495,8 @@ B200RNN_API int b200rnn_backward_fused(const b200rnn_desc* desc, const float* x,
     set_error("backward: B200RNN_FLAG_FUSED_LN and ln_gamma must be given together (as in the forward)");
     return B200RNN_ERR_INVALID;
   }
-  if (fused_ln && (d.I % 128 != 0 || d.I > 1024 || !tc_available())) {
-    set_error("backward: the fused LayerNorm needs input_size in {128,...,1024} (multiple of 128)");
+  if (fused_ln && (!(d.I == 128 || d.I == 256 || d.I == 512 || d.I == 1024) || !tc_available())) {
+    set_error("backward: the fused LayerNorm needs input_size 128, 256, 512 or 1024");
     return B200RNN_ERR_UNSUPPORTED;
   }
   if (!aligned_to(reserve, 256) || !aligned_to(scratch, 256)) {

@@ -581,21 +581,17 @@ int tc_layernorm_split(const float* src, const RowMap& rows, int R, int Cc, cons
                        float eps, float* hi, float* lo, cudaStream_t stream, float* out) {
   const bool vec = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && rows.s_outer % 4 == 0 && rows.s_inner % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15u) == 0;
-  if (!vec || Cc % 128 != 0 || Cc > 1024 || Cc < 128) {
-    set_error("layernorm_split: needs 16-byte aligned rows and a feature width in {128,...,1024} multiple of 128");
+  if (!vec || !(Cc == 128 || Cc == 256 || Cc == 512 || Cc == 1024)) {
+    set_error("layernorm_split: needs 16-byte aligned rows and a feature width of 128, 256, 512 or 1024");
     return B200RNN_ERR_UNSUPPORTED;
   }
   int blocks = (R + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   ProfScope prof(PROF_MISC, stream);
-  switch (Cc / 128) {
+  switch (Cc / 128) {  // instantiated widths: 128, 256, 512, 1024 (the reference normalises 256-d audio features)
     case 1: layernorm_split_kernel<1><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
     case 2: layernorm_split_kernel<2><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
-    case 3: layernorm_split_kernel<3><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
     case 4: layernorm_split_kernel<4><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
-    case 5: layernorm_split_kernel<5><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
-    case 6: layernorm_split_kernel<6><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
-    case 7: layernorm_split_kernel<7><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
     default: layernorm_split_kernel<8><<<blocks, 256, 0, stream>>>(src, rows, R, Cc, gamma, beta, eps, hi, lo, out); break;
   }
   B200_CUDA_CHECK(cudaGetLastError());
@@ -612,24 +608,26 @@ int launch_layernorm_bwd(const float* x, const RowMap& x_rows, const float* dy, 
                    (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15u) == 0 &&
                    (!dx || ((reinterpret_cast<uintptr_t>(dx) & 15u) == 0 && dx_rows.s_outer % 4 == 0 &&
                             dx_rows.s_inner % 4 == 0));
-  if (!vec || Cc % 128 != 0 || Cc > 1024 || Cc < 128) {
-    set_error("layernorm_bwd: needs 16-byte aligned rows and a feature width in {128,...,1024} multiple of 128");
+  if (!vec || !(Cc == 128 || Cc == 256 || Cc == 512 || Cc == 1024)) {
+    set_error("layernorm_bwd: needs 16-byte aligned rows and a feature width of 128, 256, 512 or 1024");
     return B200RNN_ERR_UNSUPPORTED;
   }
   int blocks = (R + 7) / 8;
   if (blocks > LNB_BLOCKS) blocks = LNB_BLOCKS;
   const size_t smem = (size_t)8 * 2 * Cc * sizeof(float);
   ProfScope prof(PROF_MISC, stream);
+  // 8 warps x 2 x Cc floats of per-warp column partials: 64 KB at Cc = 1024, above the 48 KB default limit
+  static bool attr[MAX_DEVICES] = {false};
+  if (!attr[current_device()]) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr[current_device()] = true;
+  }
 #define B200_LNB(NV_) \
   layernorm_bwd_kernel<NV_><<<blocks, 256, smem, stream>>>(x, x_rows, dy, R, Cc, gamma, eps, dx, dx_rows, part)
   switch (Cc / 128) {
     case 1: B200_LNB(1); break;
     case 2: B200_LNB(2); break;
-    case 3: B200_LNB(3); break;
     case 4: B200_LNB(4); break;
-    case 5: B200_LNB(5); break;
-    case 6: B200_LNB(6); break;
-    case 7: B200_LNB(7); break;
     default: B200_LNB(8); break;
   }
 #undef B200_LNB

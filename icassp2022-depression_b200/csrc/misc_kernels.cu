@@ -73,24 +73,6 @@ __global__ void dropout_split_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
-__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
-  __shared__ float tile[32][33];
-  const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
-  for (int tidx = blockIdx.x; tidx < tiles_c * tiles_r; tidx += gridDim.x) {
-    const int tr = tidx / tiles_c, tc = tidx - tr * tiles_c;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-      int r = tr * 32 + i, c = tc * 32 + threadIdx.x;
-      tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * cols + c] : 0.f;
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-      int c = tc * 32 + i, r = tr * 32 + threadIdx.x;
-      if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][i];
-    }
-    __syncthreads();
-  }
-}
-
 __global__ void bias_reduce_kernel(const float* __restrict__ part, int nslices, int mode, int H, float* db_ih,
                                    float* db_hh, int accumulate) {
   const int G = mode == B200RNN_GRU ? 3 : 4;
@@ -148,15 +130,6 @@ int launch_dropout_split(const float* in, float* out, float* hi, float* lo, size
   return B200RNN_OK;
 }
 
-int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t stream) {
-  if (rows <= 0 || cols <= 0) return B200RNN_OK;
-  int tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
-  int blocks = tiles < SMS * 4 ? tiles : SMS * 4;
-  transpose_kernel<<<blocks, dim3(32, 8), 0, stream>>>(src, dst, rows, cols);
-  B200_CUDA_CHECK(cudaGetLastError());
-  count_launch();
-  return B200RNN_OK;
-}
 
 int launch_bias_reduce(const float* part, int nslices, int mode, int H, float* db_ih, float* db_hh,
                        int accumulate, cudaStream_t stream) {

@@ -20,9 +20,6 @@ int launch_dropout(const float* in, float* out, size_t n, float p, const uint64_
 int launch_dropout_split(const float* in, float* out, float* hi, float* lo, size_t n, float p, const uint64_t* hdr,
                          uint32_t stream_id, cudaStream_t stream);
 
-// dst[c][r] = src[r][c]   (src [rows, cols] row-major)
-int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t stream);
-
 // db_ih / db_hh from the per-slice partial sums written by the backward recurrence:
 //   part [nslices][(G+1)*H]  (first G*H: sum of dGi columns; tail H: GRU sum of dn*r)
 //   GRU : db_ih = sum(part[:, :3H]);  db_hh = (sum part[:, :2H], sum part[:, 3H:4H])

@@ -780,7 +780,7 @@ def _teardown(graphs, e2e_graphs, world: int, fused=None) -> None:
     e2e_graphs.clear()
     torch.cuda.synchronize()
     if fused is not None:
-        fused.close()          # unmap the peer exchange buffers (barrier inside)
+        fused.close()          # flush a deferred update, unmap the peer exchange buffers (barrier inside)
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
@@ -843,7 +843,7 @@ def main() -> None:
     ap.add_argument("--one-stream", action="store_true",
                     help="serialise the audio and text encoder branches on one stream (default: the audio branch runs "
                          "on a second, high-priority stream = parallel branches of the CUDA graph)")
-    ap.add_argument("--exchange", choices=["auto", "peer", "nccl", "none"], default="auto",
+    ap.add_argument("--exchange", choices=["auto", "peer", "peer_async", "nccl", "none"], default="auto",
                     help="data-parallel gradient exchange of the fused step: in-kernel NVLink peer stores or NCCL")
     args = ap.parse_args()
     _protect_stdout()

@@ -42,6 +42,7 @@ SYMBOLS = (
     "b200rnn_adam",
     "b200rnn_adamw",
     "b200rnn_fuse_head",
+    "b200rnn_fuse_head_finish",
     "b200rnn_fuse_head_scratch_floats",
     "b200rnn_comm_bytes",
     "b200rnn_comm_create",
@@ -84,19 +85,19 @@ class FuseHeadArgs(ctypes.Structure):
         ("regression", c_int32),
         ("accumulate", c_int32),
         ("do_adam", c_int32),
-        ("world", c_int32), ("rank", c_int32),
+        ("world", c_int32), ("rank", c_int32), ("defer_exchange", c_int32),
         ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("grad_scale", c_float),
         ("rng_consume", c_uint64),
         ("seq_st", c_int64), ("seq_sb", c_int64),
         ("seq", c_void_p), ("h_n", c_void_p), ("w_att", c_void_p), ("b_att", c_void_p),
-        ("ctx_in", c_void_p), ("ctx_out", c_void_p),
+        ("ctx_in", c_void_p), ("ctx_out", c_void_p), ("tf_in", c_void_p),
         ("w_t", c_void_p), ("b_t", c_void_p), ("pooled", c_void_p), ("w_a", c_void_p), ("b_a", c_void_p),
         ("rng_state", c_void_p),
         ("text_feature", c_void_p), ("audio_feature", c_void_p),
         ("W", c_void_p), ("w_modal", c_void_p), ("labels", c_void_p),
         ("out", c_void_p), ("loss", c_void_p), ("dw_part", c_void_p), ("dw", c_void_p), ("ticket", c_void_p),
         ("adam_m", c_void_p), ("adam_v", c_void_p), ("adam_step", c_void_p),
-        ("comm_step", c_void_p),
+        ("comm_step", c_void_p), ("comm_done", c_void_p),
         ("comm_buf", c_void_p * 8),
     ]
 
@@ -212,6 +213,8 @@ def load() -> ctypes.CDLL:
                                   c_float, c_float, c_float, c_int, c_void_p]
     lib.b200rnn_fuse_head.restype = c_int
     lib.b200rnn_fuse_head.argtypes = [POINTER(FuseHeadArgs), c_void_p]
+    lib.b200rnn_fuse_head_finish.restype = c_int
+    lib.b200rnn_fuse_head_finish.argtypes = [POINTER(FuseHeadArgs), c_void_p]
     lib.b200rnn_fuse_head_scratch_floats.restype = c_size_t
     lib.b200rnn_fuse_head_scratch_floats.argtypes = [c_int, c_int, c_int, c_int]
     lib.b200rnn_comm_bytes.restype = c_size_t

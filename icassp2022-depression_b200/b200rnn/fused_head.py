@@ -141,7 +141,11 @@ class FusedFuseStep:
 
     Data parallel (``torch.distributed`` initialised, world > 1): ``exchange="peer"`` (default when CUDA IPC peer
     mapping works) sums the 3 KB gradient inside the same kernel through peer-mapped buffers over NVLink
-    (:class:`b200rnn.dp.PeerComm`); ``exchange="nccl"`` keeps the separate ``all_reduce`` + ``b200rnn_adamw`` launches;
+    (:class:`b200rnn.dp.PeerComm`); ``exchange="peer_async"`` additionally defers the wait for the peers, the rank-ordered
+    sum and Adam to the START of the next step on a side stream (``b200rnn_fuse_head_finish``), so a rank never idles
+    for a slower one at the end of its step - same arithmetic, same update order, but ``fc_final.0.weight`` carries a
+    step's update only once the next step has begun or :meth:`flush` was called; ``exchange="nccl"`` keeps the separate
+    ``all_reduce`` + ``b200rnn_adamw`` launches;
     ``exchange="none"`` runs a single-replica step even when a process group exists.
     """
 
@@ -150,6 +154,7 @@ class FusedFuseStep:
         import torch.distributed as dist
 
         self.concurrent_branches = bool(concurrent_branches)
+        self.split_head = bool(concurrent_branches)   # text half of the head on the text stream, before the join
         self._side = None
         self.regression = bool(getattr(model, "regression", False))
         self.C = 1 if self.regression else 2
@@ -180,21 +185,23 @@ class FusedFuseStep:
         self.rng_state = torch.tensor([(torch.initial_seed() * 2654435761 + 12345) & 0x7FFFFFFFFFFFFFFF, 0],
                                       dtype=torch.int64, device=dev)
         self.comm = None
-        if exchange not in ("auto", "peer", "nccl", "none"):
-            raise ValueError("exchange must be 'auto', 'peer', 'nccl' or 'none'")
+        if exchange not in ("auto", "peer", "peer_async", "nccl", "none"):
+            raise ValueError("exchange must be 'auto', 'peer', 'peer_async', 'nccl' or 'none'")
+        self._aux = None
+        self.comm_done = torch.zeros(1, dtype=torch.int32, device=dev)
         self.exchange = "none"
         if exchange == "none":        # single-replica step even inside an initialised process group (no collective)
             self.world, self.rank = 1, 0
         if self.world > 1:
             self.exchange = "nccl"
-            if exchange in ("auto", "peer"):
+            if exchange in ("auto", "peer", "peer_async"):
                 try:
                     from .dp import PeerComm
 
                     self.comm = PeerComm(dev, self.group)
-                    self.exchange = "peer"
+                    self.exchange = "peer_async" if exchange == "peer_async" else "peer"
                 except Exception:
-                    if exchange == "peer":
+                    if exchange in ("peer", "peer_async"):
                         raise
                 # every rank must take the same path: fall back together if any rank could not map its peers
                 ok = torch.tensor([1 if self.comm is not None else 0], device=dev)
@@ -204,53 +211,86 @@ class FusedFuseStep:
                         self.comm.close()
                     self.comm, self.exchange = None, "nccl"
 
+    def _finish_args(self) -> "_lib.FuseHeadArgs":
+        m = self.model
+        a = _lib.FuseHeadArgs(Ht=m.text_hidden_dims, Ha=m.audio_hidden_dims, regression=int(self.regression),
+                              world=self.world, rank=self.rank, defer_exchange=1,
+                              lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                              grad_scale=1.0 / self.world, W=self.w.data_ptr(), adam_m=self.m.data_ptr(),
+                              adam_v=self.v.data_ptr(), adam_step=self.step_count.data_ptr(),
+                              comm_step=self.comm.step.data_ptr(), comm_done=self.comm_done.data_ptr())
+        for r in range(self.world):
+            a.comm_buf[r] = self.comm.bufs[r]
+        return a
+
+    @torch.no_grad()
+    def flush(self) -> None:
+        """``exchange="peer_async"``: apply the update of the last step (its gradient has been sent to the peers, the
+        wait + sum + Adam normally run at the start of the NEXT step). Call before reading ``fc_final.0.weight`` -
+        evaluation, checkpointing, the end of training. No-op in every other mode and when nothing is pending."""
+        if self.exchange != "peer_async" or self.comm is None:
+            return
+        dev = self.w.device
+        a = self._finish_args()
+        with _on(dev):
+            _lib.check(_lib.load().b200rnn_fuse_head_finish(ctypes.byref(a), _stream(dev)), "b200rnn_fuse_head_finish")
+
     def close(self) -> None:
         if self.comm is not None:
+            self.flush()
             self.comm.close()
             self.comm = None
 
-    def _encoders(self, batch: FuseBatch):
-        """The two independent encoder branches (fuse_net_whole.py:347 text BiLSTM, :361 audio GRU). With
-        ``concurrent_branches`` the text branch is enqueued on a second stream (fork / join by events, captured as
-        parallel branches of the CUDA graph): the persistent GRU recurrence occupies 128 of the 148 SMs for ~2/3 of
-        the step, the text kernels fill the rest instead of waiting behind it."""
+    def _text_branch(self, batch: FuseBatch):
         m = self.model
+        seq, h_n, _ = rnn_forward_fused(batch.text.permute(1, 0, 2), m.lstm_net._flat_weights, m.lstm_net._config(),
+                                        m.lstm_net._rng_state, wcache=m.lstm_net.frozen_weight_cache())
+        return seq, h_n.contiguous()
+
+    def _audio_branch(self, batch: FuseBatch):
+        m = self.model
+        return m.lstm_net_audio.forward_ln_sum(batch.audio, None if self.regression else m.ln)
+
+    def _encoders(self, batch: FuseBatch, text_stage=None):
+        """The two independent encoder branches (fuse_net_whole.py:347 text BiLSTM, :361 audio GRU). With
+        ``concurrent_branches`` the audio branch - the critical path, 2 x 120 serial steps - is enqueued on a second,
+        high-priority stream (fork / join by events, captured as parallel branches of the CUDA graph): its persistent
+        recurrence occupies 128 of the 148 SMs for most of the step, the text kernels fill the rest instead of
+        waiting behind it. ``text_stage(seq, h_n)`` (the text half of the head kernel) runs on the text stream before
+        the join, i.e. off the critical path."""
         dev = batch.text.device
-
-        def text():
-            seq, h_n, _ = rnn_forward_fused(batch.text.permute(1, 0, 2), m.lstm_net._flat_weights,
-                                            m.lstm_net._config(), m.lstm_net._rng_state,
-                                            wcache=m.lstm_net.frozen_weight_cache())
-            return seq, h_n.contiguous()
-
         if not self.concurrent_branches:
-            seq, h_n = text()
-            pooled = m.lstm_net_audio.forward_ln_sum(batch.audio, None if self.regression else m.ln)
-            return seq, h_n, pooled
-        if self._side is None:   # the audio branch is the critical path (2 x 120 serial steps): high-priority stream
+            seq, h_n = self._text_branch(batch)
+            extra = text_stage(seq, h_n) if text_stage is not None else None
+            return seq, h_n, self._audio_branch(batch), extra
+        if self._side is None:
             self._side = torch.cuda.Stream(dev, priority=-1)
         main = torch.cuda.current_stream(dev)
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
-            pooled = m.lstm_net_audio.forward_ln_sum(batch.audio, None if self.regression else m.ln)
-        seq, h_n = text()
+            pooled = self._audio_branch(batch)
+        seq, h_n = self._text_branch(batch)
+        extra = text_stage(seq, h_n) if text_stage is not None else None
         main.wait_stream(self._side)
         pooled.record_stream(main)
-        return seq, h_n, pooled
+        return seq, h_n, pooled, extra
 
-    def _args(self, seq, h_n, pooled, tf, af) -> "_lib.FuseHeadArgs":
+    def _args(self, seq, h_n, pooled, tf, af, tf_in=None) -> "_lib.FuseHeadArgs":
+        """Argument block of ``b200rnn_fuse_head``. ``pooled=None``: text stage only; ``tf_in``: text stage already done."""
         m = self.model
         T, B, H2 = seq.shape
-        assert seq.stride(2) == 1 and pooled.is_contiguous()
+        assert seq.stride(2) == 1 and (pooled is None or pooled.is_contiguous())
         att, lt, la = m.attention_layer[0], m.fc_out[1], m.fc_audio[1]
         _require_cuda(("attention weight", att.weight), ("fc_out weight", lt.weight), ("fc_audio weight", la.weight))
         return _lib.FuseHeadArgs(
             B=B, T=T, Ht=m.text_hidden_dims, Ha=m.audio_hidden_dims, n_states=h_n.shape[0],
             training=int(m.training), p=float(m.dropout), regression=int(self.regression),
-            seq_st=seq.stride(0), seq_sb=seq.stride(1), seq=seq.data_ptr(), h_n=h_n.data_ptr(),
+            seq_st=seq.stride(0), seq_sb=seq.stride(1), seq=seq.data_ptr() if tf_in is None else None,
+            h_n=h_n.data_ptr(), tf_in=tf_in.data_ptr() if tf_in is not None else None,
             w_att=att.weight.data_ptr(), b_att=att.bias.data_ptr(), w_t=lt.weight.data_ptr(), b_t=lt.bias.data_ptr(),
-            pooled=pooled.data_ptr(), w_a=la.weight.data_ptr(), b_a=la.bias.data_ptr(),
-            text_feature=tf.data_ptr(), audio_feature=af.data_ptr())
+            pooled=pooled.data_ptr() if pooled is not None else None, w_a=la.weight.data_ptr(), b_a=la.bias.data_ptr(),
+            text_feature=tf.data_ptr() if tf_in is None else None,
+            audio_feature=af.data_ptr() if af is not None else None)
 
     @torch.no_grad()
     def features(self, batch: FuseBatch):
@@ -260,7 +300,7 @@ class FusedFuseStep:
         lib = _lib.load()
         _require_cuda(("batch.audio", batch.audio), ("batch.text", batch.text))
         dev = batch.text.device
-        seq, h_n, pooled = self._encoders(batch)
+        seq, h_n, pooled, _ = self._encoders(batch)
         B = seq.shape[1]
         tf = torch.empty(B, m.text_hidden_dims, device=dev)
         af = torch.empty(B, m.audio_hidden_dims, device=dev)
@@ -282,8 +322,29 @@ class FusedFuseStep:
         m = self.model
         _require_cuda(("labels", labels), ("batch.audio", batch.audio), ("batch.text", batch.text))
         dev = batch.text.device
-        seq, h_n, pooled = self._encoders(batch)
-        B = seq.shape[1]
+        B = batch.text.shape[0]
+        tf = torch.empty(B, m.text_hidden_dims, device=dev)
+        if self.exchange == "peer_async":
+            # the previous step's gradient sum + Adam, beside this step's encoders: a rank that is ahead of its peers
+            # waits HERE, on a stream nothing else hangs on, instead of at the end of its head kernel
+            if self._aux is None:
+                self._aux = torch.cuda.Stream(dev)
+            main0 = torch.cuda.current_stream(dev)
+            self._aux.wait_stream(main0)
+            fa = self._finish_args()
+            with torch.cuda.stream(self._aux), _on(dev):
+                _lib.check(lib.b200rnn_fuse_head_finish(ctypes.byref(fa), _stream(dev)), "b200rnn_fuse_head_finish")
+
+        def text_stage(seq, h_n):
+            # the text half of the head (attention pooling + fc_out) on the text branch's stream, while the audio
+            # recurrence is still running; reads the same {seed, offset} the final launch will read and then advance
+            a0 = self._args(seq, h_n, None, tf, None)
+            a0.rng_state = self.rng_state.data_ptr()
+            with _on(dev):
+                _lib.check(lib.b200rnn_fuse_head(ctypes.byref(a0), _stream(dev)), "b200rnn_fuse_head (text stage)")
+            return True
+
+        seq, h_n, pooled, _ = self._encoders(batch, text_stage if self.split_head else None)
         # the kernel reads `const int64_t labels[B]` (classification) / `const float labels[B]` (regression): anything
         # else (int32 from numpy, a strided view) would be silently misread, so it is converted here; class indices
         # outside {0,1} poison the loss with NaN on the device
@@ -292,14 +353,13 @@ class FusedFuseStep:
             labels = labels.to(want).contiguous()
         if labels.numel() != B:
             raise ValueError(f"FusedFuseStep: {labels.numel()} labels for a batch of {B}")
-        tf = torch.empty(B, m.text_hidden_dims, device=dev)
         af = torch.empty(B, m.audio_hidden_dims, device=dev)
         out = torch.empty(B, self.C, dtype=torch.float32, device=dev)
         need = int(lib.b200rnn_fuse_head_scratch_floats(B, m.text_hidden_dims, m.audio_hidden_dims,
                                                         int(self.regression)))
         if self._dw_part is None or self._dw_part.numel() < need:
             self._dw_part = torch.empty(need, device=dev)
-        a = self._args(seq, h_n, pooled, tf, af)
+        a = self._args(seq, h_n, pooled, tf, af, tf_in=tf if self.split_head else None)
         a.W = self.w.data_ptr()
         a.w_modal = m.modal_attn.weight.data_ptr() if self.regression else None
         a.labels = labels.data_ptr()
@@ -315,11 +375,15 @@ class FusedFuseStep:
         a.grad_scale = 1.0 / self.world
         a.world, a.rank = 1, 0
         a.do_adam = 1
-        if self.exchange == "peer":
+        if self.exchange in ("peer", "peer_async"):
             a.world, a.rank = self.world, self.rank
             a.comm_step = self.comm.step.data_ptr()
+            a.comm_done = self.comm_done.data_ptr()
+            a.defer_exchange = 1 if self.exchange == "peer_async" else 0
             for r in range(self.world):
                 a.comm_buf[r] = self.comm.bufs[r]
+            if self.exchange == "peer_async":
+                torch.cuda.current_stream(dev).wait_stream(self._aux)   # W must carry the previous step's update
         elif self.exchange == "nccl":
             a.do_adam = 0
         with _on(dev):

@@ -114,6 +114,72 @@ __device__ __forceinline__ void matvec_rows(const float* __restrict__ W, const f
   }
 }
 
+// ---- one-shot peer exchange, two halves (see the file header) -------------------------------------------------------
+// send: g[0..n) -> slot [parity][rank] of every rank's buffer, then the step tag into flag [parity][rank] there
+__device__ __forceinline__ void peer_send(const b200rnn_fuse_head_args& a, const float* g, int n, uint32_t step, int tid) {
+  const uint32_t par = step & 1u, tag = step + 1u;
+  for (int idx = tid; idx < a.world * n; idx += HEAD_THREADS) {
+    const int dst = idx / n, i = idx - dst * n;
+    float* slot = reinterpret_cast<float*>(static_cast<unsigned char*>(a.comm_buf[dst]) + COMM_DATA_OFF) +
+                  ((size_t)par * COMM_MAX_WORLD + a.rank) * COMM_PAYLOAD;
+    slot[i] = g[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < a.world) {
+    uint32_t* f = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(a.comm_buf[tid]) + COMM_FLAG_OFF) +
+                  par * COMM_MAX_WORLD + a.rank;
+    st_release_sys(f, tag);
+  }
+}
+// wait for every peer's slot of `step`, then out[i] = sum over ranks in rank order (identical on every rank)
+__device__ __forceinline__ void peer_wait_sum(const b200rnn_fuse_head_args& a, float* out, int n, uint32_t step, int tid) {
+  const uint32_t par = step & 1u, tag = step + 1u;
+  if (tid < a.world) {
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(static_cast<unsigned char*>(a.comm_buf[a.rank]) + COMM_FLAG_OFF) +
+                           par * COMM_MAX_WORLD + tid;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine) != tag) {
+      if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a peer died or the protocol is broken
+    }
+  }
+  __syncthreads();
+  const float* slots = reinterpret_cast<const float*>(static_cast<unsigned char*>(a.comm_buf[a.rank]) + COMM_DATA_OFF) +
+                       (size_t)par * COMM_MAX_WORLD * COMM_PAYLOAD;
+  for (int i = tid; i < n; i += HEAD_THREADS) {
+    float s = 0.f;
+    for (int r = 0; r < a.world; ++r) s += __ldcv(slots + (size_t)r * COMM_PAYLOAD + i);  // rank order on every rank
+    out[i] = s;
+  }
+  __syncthreads();
+}
+
+// Deferred half of the exchange: applies the update of the oldest step that was sent but not applied yet (if any).
+__global__ void __launch_bounds__(HEAD_THREADS) fuse_head_finish_kernel(const b200rnn_fuse_head_args a) {
+  __shared__ float g[COMM_PAYLOAD];
+  const int tid = threadIdx.x;
+  const int n = (a.regression ? 1 : 2) * (a.Ht + a.Ha);
+  const uint32_t done = *a.comm_done, sent = *a.comm_step;
+  if (done == sent) return;  // nothing pending (first step, or already flushed)
+  peer_wait_sum(a, g, n, done, tid);
+  const float t = *a.adam_step + 1.f;
+  const float bc1 = 1.f - powf(a.beta1, t), bc2 = 1.f - powf(a.beta2, t);
+  const float step_size = a.lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (int i = tid; i < n; i += HEAD_THREADS) {
+    const float gi = g[i] * a.grad_scale;
+    const float mi = a.beta1 * a.adam_m[i] + (1.f - a.beta1) * gi;
+    const float vi = a.beta2 * a.adam_v[i] + (1.f - a.beta2) * gi * gi;
+    a.adam_m[i] = mi;
+    a.adam_v[i] = vi;
+    a.W[i] = a.W[i] - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + a.eps);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    *a.adam_step = t;
+    *a.comm_done = done + 1u;
+  }
+}
+
 __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_fuse_head_args a) {
   constexpr int R = HEAD_ROWS;
   extern __shared__ __align__(16) float sm[];
@@ -144,7 +210,13 @@ __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_f
   }
 
   // ---------------- text branch: attention pooling (text_bilstm_whole.py:74-99) ----------------------------------
-  if (a.seq) {
+  if (a.tf_in) {
+    // text stage already done by an earlier launch on the text branch's stream: take its text_feature as is
+    for (int idx = tid; idx < R * Ht; idx += HEAD_THREADS) {
+      const int r = idx / Ht, j = idx - r * Ht, b = b0 + r;
+      feat[r * F + j] = (b < B) ? a.tf_in[(size_t)b * Ht + j] : 0.f;
+    }
+  } else if (a.seq) {
     for (int idx = tid; idx < R * Ht; idx += HEAD_THREADS) {
       const int r = idx / Ht, j = idx - r * Ht, b = b0 + r;
       float s = 0.f;
@@ -209,19 +281,21 @@ __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_f
     }
   }
   // ---------------- audio branch input: time-summed GRU output with fc_audio[0] Dropout ---------------------------
-  for (int idx = tid; idx < R * Ha; idx += HEAD_THREADS) {
-    const int r = idx / Ha, j = idx - r * Ha, b = b0 + r;
-    float v = (b < B) ? a.pooled[(size_t)b * Ha + j] : 0.f;
-    if (drop && b < B) v *= keep_scale(seed, offset, 2, (size_t)b * Ha + j, thr, scale);
-    xa[idx] = v;
-  }
+  if (a.pooled)
+    for (int idx = tid; idx < R * Ha; idx += HEAD_THREADS) {
+      const int r = idx / Ha, j = idx - r * Ha, b = b0 + r;
+      float v = (b < B) ? a.pooled[(size_t)b * Ha + j] : 0.f;
+      if (drop && b < B) v *= keep_scale(seed, offset, 2, (size_t)b * Ha + j, thr, scale);
+      xa[idx] = v;
+    }
   __syncthreads();
   // ---------------- the two Linear+ReLU heads, then their output Dropout ------------------------------------------
-  matvec_rows<R, true>(a.w_t, a.b_t, ctx, Ht, feat, F, Ht, Ht, warp, nw, lane);
-  matvec_rows<R, true>(a.w_a, a.b_a, xa, Ha, feat + Ht, F, Ha, Ha, warp, nw, lane);
+  if (!a.tf_in) matvec_rows<R, true>(a.w_t, a.b_t, ctx, Ht, feat, F, Ht, Ht, warp, nw, lane);
+  if (a.pooled) matvec_rows<R, true>(a.w_a, a.b_a, xa, Ha, feat + Ht, F, Ha, Ha, warp, nw, lane);
   __syncthreads();
   for (int idx = tid; idx < R * F; idx += HEAD_THREADS) {
     const int r = idx / F, j = idx - r * F, b = b0 + r;
+    if ((j < Ht) ? (a.tf_in != nullptr) : (a.pooled == nullptr)) continue;  // half not produced by this launch
     float v = feat[idx];
     if (b < B) {
       if (drop)
@@ -352,37 +426,15 @@ __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_f
     if (lane == 0) a.dw[C * F] = l;
   }
   __syncthreads();
+  bool apply_update = true;
   if (a.world > 1) {
-    uint32_t* my_flags = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(a.comm_buf[a.rank]) + COMM_FLAG_OFF);
     const uint32_t step = *a.comm_step;  // device-resident: a captured graph advances it at every replay
-    const uint32_t par = step & 1u, tag = step + 1u;
     const int NX = C * F;  // the loss stays local (each rank reports its own shard's loss, like the reference would)
-    for (int idx = tid; idx < a.world * NX; idx += HEAD_THREADS) {
-      const int dst = idx / NX, i = idx - dst * NX;
-      float* slot = reinterpret_cast<float*>(static_cast<unsigned char*>(a.comm_buf[dst]) + COMM_DATA_OFF) +
-                    ((size_t)par * COMM_MAX_WORLD + a.rank) * COMM_PAYLOAD;
-      slot[i] = a.dw[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < a.world) {
-      uint32_t* f = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(a.comm_buf[tid]) + COMM_FLAG_OFF) +
-                    par * COMM_MAX_WORLD + a.rank;
-      st_release_sys(f, tag);
-      // wait for peer `tid`'s gradient of this step
-      const uint32_t* mine = my_flags + par * COMM_MAX_WORLD + tid;
-      const long long t0 = clock64();
-      while (ld_acquire_sys(mine) != tag) {
-        if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a peer died or the protocol is broken
-      }
-    }
-    __syncthreads();
-    const float* slots = reinterpret_cast<const float*>(static_cast<unsigned char*>(a.comm_buf[a.rank]) + COMM_DATA_OFF) +
-                         (size_t)par * COMM_MAX_WORLD * COMM_PAYLOAD;
-    for (int i = tid; i < NX; i += HEAD_THREADS) {
-      float s = 0.f;
-      for (int r = 0; r < a.world; ++r) s += __ldcv(slots + (size_t)r * COMM_PAYLOAD + i);  // rank order on every rank
-      a.dw[i] = s;
+    peer_send(a, a.dw, NX, step, tid);
+    if (a.defer_exchange) {
+      apply_update = false;  // b200rnn_fuse_head_finish waits, sums and applies Adam (next step, beside the encoders)
+    } else {
+      peer_wait_sum(a, a.dw, NX, step, tid);
     }
     if (tid == 0) *a.comm_step = step + 1u;
     __syncthreads();
@@ -392,7 +444,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) fuse_head_kernel(const b200rnn_f
     *a.ticket = 0u;  // re-armed for the next launch (graph replay)
     if (drop && a.rng_state) a.rng_state[1] = offset + a.rng_consume;
   }
-  if (a.do_adam) {  // torch.optim.Adam (no weight decay, no amsgrad); grad_scale = 1/world (mean over the global batch)
+  if (a.do_adam && apply_update) {  // torch.optim.Adam (no weight decay, no amsgrad); grad_scale = 1/world
     const float t = *a.adam_step + 1.f;
     const float bc1 = 1.f - powf(a.beta1, t), bc2 = 1.f - powf(a.beta2, t);
     const float step_size = a.lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
@@ -440,9 +492,10 @@ B200RNN_API int b200rnn_fuse_head(const b200rnn_fuse_head_args* args, void* stre
     return B200RNN_ERR_UNSUPPORTED;
   }
   if (a.B == 0) return B200RNN_OK;
-  const bool have_text = a.seq ? (a.h_n && a.w_att && a.b_att && a.T >= 1 && a.n_states >= 1) : (a.ctx_in != nullptr);
-  if (!have_text || !a.pooled || !a.w_t || !a.b_t || !a.w_a || !a.b_a) {
-    set_error("fuse_head: null pointer argument");
+  const bool have_text = a.tf_in ? true
+                         : (a.seq ? (a.h_n && a.w_att && a.b_att && a.T >= 1 && a.n_states >= 1) : (a.ctx_in != nullptr));
+  if (!have_text || (!a.tf_in && (!a.w_t || !a.b_t)) || (a.pooled && (!a.w_a || !a.b_a)) || (!a.pooled && a.W)) {
+    set_error("fuse_head: null pointer argument (or the loss stage without the audio stage)");
     return B200RNN_ERR_INVALID;
   }
   if (a.training && a.p > 0.f && !a.rng_state) {
@@ -461,7 +514,7 @@ B200RNN_API int b200rnn_fuse_head(const b200rnn_fuse_head_args* args, void* stre
     const int C = a.regression ? 1 : 2;
     if (a.world > 1) {
       if (a.world > COMM_MAX_WORLD || a.rank < 0 || a.rank >= a.world || !a.comm_step ||
-          C * (a.Ht + a.Ha) > COMM_PAYLOAD) {
+          C * (a.Ht + a.Ha) > COMM_PAYLOAD || (a.defer_exchange && !a.comm_done)) {
         set_error("fuse_head: bad peer-exchange arguments (world=%d rank=%d)", a.world, a.rank);
         return B200RNN_ERR_INVALID;
       }
@@ -472,7 +525,7 @@ B200RNN_API int b200rnn_fuse_head(const b200rnn_fuse_head_args* args, void* stre
         }
     }
   }
-  const size_t smem = head_smem_floats(a.B, a.Ht, a.Ha, a.seq ? a.T : 0, a.W != nullptr) * sizeof(float);
+  const size_t smem = head_smem_floats(a.B, a.Ht, a.Ha, (a.seq && !a.tf_in) ? a.T : 0, a.W != nullptr) * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("fuse_head: widths too large for one CTA");
     return B200RNN_ERR_UNSUPPORTED;
@@ -484,6 +537,30 @@ B200RNN_API int b200rnn_fuse_head(const b200rnn_fuse_head_args* args, void* stre
   }
   const int grid = (a.B + HEAD_ROWS - 1) / HEAD_ROWS;
   fuse_head_kernel<<<grid, HEAD_THREADS, smem, static_cast<cudaStream_t>(stream_)>>>(a);
+  B200_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return B200RNN_OK;
+}
+
+B200RNN_API int b200rnn_fuse_head_finish(const b200rnn_fuse_head_args* args, void* stream_) {
+  if (!args || args->struct_bytes != sizeof(b200rnn_fuse_head_args)) {
+    set_error("fuse_head_finish: null or mismatched argument block");
+    return B200RNN_ERR_INVALID;
+  }
+  const b200rnn_fuse_head_args& a = *args;
+  if (a.world <= 1) return B200RNN_OK;  // nothing is ever deferred without peers
+  const int C = a.regression ? 1 : 2;
+  if (a.world > COMM_MAX_WORLD || a.rank < 0 || a.rank >= a.world || !a.comm_step || !a.comm_done || !a.W || !a.adam_m ||
+      !a.adam_v || !a.adam_step || C * (a.Ht + a.Ha) > COMM_PAYLOAD) {
+    set_error("fuse_head_finish: bad argument");
+    return B200RNN_ERR_INVALID;
+  }
+  for (int r = 0; r < a.world; ++r)
+    if (!a.comm_buf[r]) {
+      set_error("fuse_head_finish: peer buffer %d is not mapped", r);
+      return B200RNN_ERR_INVALID;
+    }
+  fuse_head_finish_kernel<<<1, HEAD_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(a);
   B200_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return B200RNN_OK;

@@ -258,6 +258,9 @@ B200RNN_API int b200rnn_adamw(float* p, const float* g, float* m, float* v, floa
  *
  * All pointers are device pointers. Stages are switched by which pointers are set:
  *   seq != NULL            : attention pooling from the BiLSTM output (else ctx_in [B,Ht] is the attention context)
+ *   tf_in != NULL          : text stage done by an earlier launch (its text_feature output); skips attention + fc_out
+ *   pooled == NULL         : text stage only (requires W == NULL): lets the text half run on the text branch's stream
+ *                            while the audio encoder is still busy, the final launch then takes tf_in
  *   W   != NULL            : output + loss + gradient (+ exchange when world > 1) (+ Adam when do_adam); W == NULL
  *                            stops after text_feature / audio_feature
  * Dropout: Philox streams 0,1 (text head in/out) and 2,3 (audio head in/out) keyed by rng_state = {seed, offset}
@@ -276,6 +279,9 @@ typedef struct b200rnn_fuse_head_args {
   int32_t accumulate;     /* dw += gradient instead of dw = gradient                                            */
   int32_t do_adam;        /* apply the Adam update to W in the same launch                                      */
   int32_t world, rank;    /* data-parallel ranks (1 = no exchange) and this rank                                */
+  int32_t defer_exchange; /* world > 1: 1 = send this step's gradient to the peers and return; the wait for theirs, the
+                             rank-ordered sum and Adam are done by b200rnn_fuse_head_finish (normally enqueued at the
+                             START of the next step beside the encoders), so a rank never idles for a slower one */
   float lr, beta1, beta2, eps, grad_scale; /* Adam hyper-parameters; grad_scale = 1/world                        */
   uint64_t rng_consume;   /* Philox offset advance per call: ceil(B*max(Ht,Ha)/4)                               */
   int64_t seq_st, seq_sb; /* element strides of seq: seq[t*seq_st + b*seq_sb + c], c in [0, 2*Ht)              */
@@ -285,6 +291,8 @@ typedef struct b200rnn_fuse_head_args {
   const float* b_att;     /* attention_layer.0.bias [Ht]                                                        */
   const float* ctx_in;    /* [B,Ht] attention context when seq == NULL                                          */
   float* ctx_out;         /* optional [B,Ht]: the attention context before Dropout                              */
+  const float* tf_in;     /* [B,Ht] text_feature computed by an earlier launch of this entry point (text stage on its
+                             own stream, see below): the text stage is skipped entirely                         */
   const float* w_t;       /* fc_out.1.weight [Ht,Ht]                                                            */
   const float* b_t;       /* fc_out.1.bias [Ht]                                                                 */
   const float* pooled;    /* [B,Ha] time-summed GRU output                                                      */
@@ -305,11 +313,16 @@ typedef struct b200rnn_fuse_head_args {
   float* adam_v;
   float* adam_step;       /* device float counting completed steps                                              */
   uint32_t* comm_step;    /* world > 1: device uint32 step counter of the exchange (zero-initialised)           */
+  uint32_t* comm_done;    /* defer_exchange: device uint32 count of steps whose update has been applied (zero-init.) */
   void* comm_buf[B200RNN_COMM_MAX_WORLD]; /* world > 1: every rank's exchange buffer as mapped in THIS process    */
 } b200rnn_fuse_head_args;
 
 B200RNN_API size_t b200rnn_fuse_head_scratch_floats(int B, int Ht, int Ha, int regression);
 B200RNN_API int b200rnn_fuse_head(const b200rnn_fuse_head_args* args, void* stream);
+/* Second half of a deferred exchange (defer_exchange = 1): if a step's gradient has been sent but not applied yet, wait
+ * for every peer's slot of that step, add the slots in rank order and apply Adam to W; otherwise do nothing. Uses the
+ * W / adam_* / lr.. / grad_scale / world / rank / comm_* fields of the same argument block. One tiny launch. */
+B200RNN_API int b200rnn_fuse_head_finish(const b200rnn_fuse_head_args* args, void* stream);
 
 /*
  * Exchange buffers of the one-shot gradient exchange (setup path; the only allocation the library ever makes, done

@@ -8,7 +8,9 @@ inside b200rnn_fuse_head) and once with exchange="nccl" (ncclAllReduce + b200rnn
 rank 0 additionally replays the GLOBAL batch on one GPU (gradient of the mean over the global batch). Checks:
   * all ranks end with bit-identical fc_final.0.weight under "peer" (same summation order everywhere),
   * "peer" == "nccl" == single-GPU global batch to 1e-7,
-  * a CUDA-graph capture of the peer step replays correctly (device-resident step counter / parity).
+  * a CUDA-graph capture of the peer step replays correctly (device-resident step counter / parity),
+  * exchange="peer_async" (gradient sent in step s, summed + applied at the start of step s+1, flush() at the end)
+    ends with the same weights, eagerly and as a replayed graph.
 Prints one JSON line on rank 0; exit code 0 = all checks passed.
 """
 import copy
@@ -43,6 +45,7 @@ def main():
         m = copy.deepcopy(base)
         st = b200rnn.FusedFuseStep(m, lr=lr, exchange=exchange)
         assert st.exchange == exchange, (st.exchange, exchange)
+        flush = st.flush
         if not use_graph:
             for s in range(steps):
                 st(b200rnn.FuseBatch(audio[s, sl].to(dev), text[s, sl].to(dev)), labels[s, sl].to(dev))
@@ -61,6 +64,7 @@ def main():
                 gr.replay()
             # the capture itself does not execute: steps 1..4 ran => 5 steps in total with the eager one
             del gr
+        flush()                       # peer_async: the last step's update is still pending
         torch.cuda.synchronize()
         w = m.fc_final[0].weight.detach().clone()
         st.close()
@@ -69,12 +73,16 @@ def main():
     w_peer = run("peer")
     w_nccl = run("nccl")
     w_graph = run("peer", use_graph=True)
+    w_async = run("peer_async")
+    w_async_graph = run("peer_async", use_graph=True)
     gathered = [torch.empty_like(w_peer) for _ in range(world)]
     dist.all_gather(gathered, w_peer)
     res = {"world": world}
     res["peer_identical_across_ranks"] = all(torch.equal(gathered[0], x) for x in gathered)
     res["peer_vs_nccl_max_abs"] = (w_peer - w_nccl).abs().max().item()
     res["graph_vs_eager_max_abs"] = (w_graph - w_peer).abs().max().item()
+    res["async_vs_sync_max_abs"] = (w_async - w_peer).abs().max().item()
+    res["async_graph_vs_sync_max_abs"] = (w_async_graph - w_peer).abs().max().item()
     if rank == 0:
         m = copy.deepcopy(base)
         st = b200rnn.FusedFuseStep(m, lr=lr, exchange="none")      # single-GPU replay of the global batch
@@ -84,7 +92,8 @@ def main():
         res["peer_vs_single_gpu_global_batch_max_abs"] = (w_peer - m.fc_final[0].weight.detach()).abs().max().item()
         res["weight_moved"] = (w_peer - base.fc_final[0].weight.detach()).abs().max().item()
         ok = (res["peer_identical_across_ranks"] and res["peer_vs_nccl_max_abs"] <= 1e-7 and
-              res["graph_vs_eager_max_abs"] <= 1e-7 and res["peer_vs_single_gpu_global_batch_max_abs"] <= 1e-7 and
+              res["graph_vs_eager_max_abs"] <= 1e-7 and res["async_vs_sync_max_abs"] <= 1e-7 and
+              res["async_graph_vs_sync_max_abs"] <= 1e-7 and res["peer_vs_single_gpu_global_batch_max_abs"] <= 1e-7 and
               res["weight_moved"] > 1e-4)
         res["ok"] = bool(ok)
         print(json.dumps(res), flush=True)

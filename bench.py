@@ -487,7 +487,8 @@ def run_ours(args) -> None:
     else:                   # the same step on the library's fused head kernel (b200rnn.FusedFuseStep): the gradient
         #                     exchange across ranks happens inside that kernel over NVLink peer stores ("peer") or,
         #                     with --exchange nccl, as a separate ncclAllReduce + Adam launch
-        fused = b200rnn.FusedFuseStep(model, lr=LR, exchange=args.exchange, concurrent_branches=not args.one_stream)
+        fused = b200rnn.FusedFuseStep(model, lr=LR, exchange=args.exchange, concurrent_branches=not args.one_stream,
+                                      allow_fallback=True)   # no CUDA IPC peer mapping -> ncclAllReduce, all ranks together
         _log(f"rank {rank}: gradient exchange = {fused.exchange}; numa binding {numa}")
 
     # ---- synthetic shards: rank r owns its own 128 sequences of the global batch (weak scaling) -------
@@ -843,8 +844,10 @@ def main() -> None:
     ap.add_argument("--one-stream", action="store_true",
                     help="serialise the audio and text encoder branches on one stream (default: the audio branch runs "
                          "on a second, high-priority stream = parallel branches of the CUDA graph)")
-    ap.add_argument("--exchange", choices=["auto", "peer", "peer_async", "nccl", "none"], default="auto",
-                    help="data-parallel gradient exchange of the fused step: in-kernel NVLink peer stores or NCCL")
+    ap.add_argument("--exchange", choices=["auto", "peer", "peer_async", "nccl", "none"], default="peer_async",
+                    help="data-parallel gradient exchange of the fused step: in-kernel NVLink peer stores (peer: wait at "
+                         "the end of the step; peer_async: send now, sum + Adam at the start of the next step beside "
+                         "the encoders, flushed after the last step) or NCCL")
     args = ap.parse_args()
     _protect_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -150,7 +150,8 @@ class FusedFuseStep:
     """
 
     def __init__(self, model, lr: float = 8e-6, betas=(0.9, 0.999), eps: float = 1e-8, bucket=None,
-                 process_group=None, exchange: str = "auto", concurrent_branches: bool = True):
+                 process_group=None, exchange: str = "auto", concurrent_branches: bool = True,
+                 allow_fallback: bool = False):
         import torch.distributed as dist
 
         self.concurrent_branches = bool(concurrent_branches)
@@ -201,7 +202,7 @@ class FusedFuseStep:
                     self.comm = PeerComm(dev, self.group)
                     self.exchange = "peer_async" if exchange == "peer_async" else "peer"
                 except Exception:
-                    if exchange in ("peer", "peer_async"):
+                    if exchange in ("peer", "peer_async") and not allow_fallback:
                         raise
                 # every rank must take the same path: fall back together if any rank could not map its peers
                 ok = torch.tensor([1 if self.comm is not None else 0], device=dev)

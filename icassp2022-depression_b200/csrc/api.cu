@@ -124,7 +124,8 @@ struct ScratchLayout {
   // backward
   size_t b_dgates[2], b_dghn[2], b_wt[2], b_bpart[2], b_dy, b_gemm;
   size_t b_gemm_bytes;
-  // tcgen05 backward GEMMs: split / transposed-split operands (hi at the offset, lo right behind it)
+  // tcgen05 backward GEMMs: dense TF32 hi/lo splits of the operands (hi at the offset, lo right behind it); the names
+  // keep their round-1 "T" although nothing is transposed any more (MN-major operands, gemm_tc.cu)
   size_t b_tc_dg, b_tc_dgT, b_tc_hnT, b_tc_xT, b_tc_yT, b_tc_wT, b_tc_part;
   size_t b_tc_part_bytes;
   long long b_ldk;  // leading dimension of the transposed operands: T*B rounded up to a multiple of 4
@@ -567,11 +568,15 @@ B200RNN_API int b200rnn_backward_fused(const b200rnn_desc* desc, const float* x,
     // ---- tcgen05 3xTF32 path for the wgrad / dgrad GEMMs (falls back to the FFMA kernel per GEMM) -------------
     const long long ldk = sl.b_ldk;
     const bool tc_l = tc_available() && (Il % 128 == 0);
-    float* xT = S + sl.b_tc_xT;  // [Il][ldk] hi, then lo
-    if (tc_l) {  // X_l^T, shared by both directions
-      rc = tc_split_transpose(in, in_rows, (int)d.TB, Il, xT, xT + (size_t)Il * ldk, ldk, st);
+    // Operands whose contraction index (t,b) is their ROW index - X_l, dG, h_prev, dn*r - go to the tensor cores as
+    // MN-major tiles (gemm_tc.cu): they only need the dense TF32 hi/lo split, no transposing pass (round 1 transposed
+    // every one of them: 10 passes, 8 % of the c2 train step).
+    float* xS = S + sl.b_tc_xT;  // [TB][Il] hi, then lo
+    if (tc_l) {  // X_l, shared by both directions
+      rc = tc_split(in, in_rows, (int)d.TB, Il, xS, xS + d.TB * (size_t)Il, st);
       if (rc) return rc;
     }
+    (void)ldk;
     for (int k = 0; k < d.D; ++k) {
       const float* const* pp = params + (size_t)(l * d.D + k) * 4;
       float* const* gp = dparams + (size_t)(l * d.D + k) * 4;
@@ -584,55 +589,16 @@ B200RNN_API int b200rnn_backward_fused(const b200rnn_desc* desc, const float* x,
       }
       bool done_dwih = (dw_ih == nullptr), done_dwhh = (dw_hh == nullptr), done_dx = !want_dx;
       if (tc_l) {
-        float* dGT = S + sl.b_tc_dgT;  // [GH][ldk]
-        float* hnT = S + sl.b_tc_hnT;  // [H][ldk]   (GRU: dn * r)
-        const TcOperand opX{xT, xT + (size_t)Il * ldk, ldk};
+        float* dGs = S + sl.b_tc_dg;   // [TB][GH] hi, then lo: MN-major A of the wgrads AND K-major A of the dgrad
+        float* hnS = S + sl.b_tc_hnT;  // [TB][H]   (GRU: dn * r)
+        const TcOperand opX{xS, xS + d.TB * (size_t)Il, (long long)Il, true};
         // the tcgen05 epilogue stores float4: a gradient target that is not 16-byte aligned (a view into a caller's
         // flat bucket behind an odd-sized tensor) takes the FFMA GEMM below instead of failing
-        const bool tc_wih = dw_ih && aligned_to(dw_ih, 16), tc_whh = dw_hh && aligned_to(dw_hh, 16);
-        if (tc_wih || tc_whh) {
-          rc = tc_split_transpose(dG, simple_rows((long long)d.GH), (int)d.TB, (int)d.GH, dGT, dGT + d.GH * ldk, ldk, st);
-          if (rc) return rc;
-        }
-        if (tc_wih) {  // dW_ih[GH, Il] = dGi^T[GH, TB] * X_l^T[Il, TB]^T
-          const TcOperand opA{dGT, dGT + d.GH * ldk, ldk};
-          rc = tc_gemm_presplit(opA, opX, (int)d.GH, Il, (int)d.TB, dw_ih, simple_rows(Il), nullptr, nullptr, 0,
-                                accumulate, S + sl.b_tc_part, sl.b_tc_part_bytes, st);
-          if (rc) return rc;
-          done_dwih = true;
-        }
-        if (tc_whh && d.T > 1 && d.B % 4 == 0) {
-          // dW_hh = sum_t dGh[t]^T h_{prev(t)}: columns of the transposed operands are (t,b) flattened time-major,
-          // so the one-step shift is a column offset of B (forward: dG[t] with y[t-1]; reverse: dG[t] with y[t+1])
-          float* yT = S + sl.b_tc_yT;  // [H][ldk]
-          rc = tc_split_transpose(bp.y + (long long)k * d.H, tb_rows(bp.y_st, bp.y_sb, d.B), (int)d.TB, d.H, yT,
-                                  yT + (size_t)d.H * ldk, ldk, st);
-          if (rc) return rc;
-          const int Kp = (d.T - 1) * d.B;
-          const size_t offA = (k == 0) ? (size_t)d.B : 0, offY = (k == 0) ? 0 : (size_t)d.B;
-          const TcOperand opY{yT + offY, yT + (size_t)d.H * ldk + offY, ldk};
-          if (d.mode == B200RNN_LSTM) {
-            const TcOperand opA{dGT + offA, dGT + d.GH * ldk + offA, ldk};
-            rc = tc_gemm_presplit(opA, opY, (int)d.GH, d.H, Kp, dw_hh, simple_rows(d.H), nullptr, nullptr, 0,
-                                  accumulate, S + sl.b_tc_part, sl.b_tc_part_bytes, st);
-            if (rc) return rc;
-          } else {
-            rc = tc_split_transpose(dHN, simple_rows((long long)d.H), (int)d.TB, d.H, hnT, hnT + (size_t)d.H * ldk, ldk, st);
-            if (rc) return rc;
-            const TcOperand opRZ{dGT + offA, dGT + d.GH * ldk + offA, ldk};  // rows [0, 2H): r and z gates
-            rc = tc_gemm_presplit(opRZ, opY, 2 * d.H, d.H, Kp, dw_hh, simple_rows(d.H), nullptr, nullptr, 0,
-                                  accumulate, S + sl.b_tc_part, sl.b_tc_part_bytes, st);
-            if (rc) return rc;
-            const TcOperand opN{hnT + offA, hnT + (size_t)d.H * ldk + offA, ldk};  // n rows use dn * r
-            rc = tc_gemm_presplit(opN, opY, d.H, d.H, Kp, dw_hh + (size_t)2 * d.H * d.H, simple_rows(d.H), nullptr,
-                                  nullptr, 0, accumulate, S + sl.b_tc_part, sl.b_tc_part_bytes, st);
-            if (rc) return rc;
-          }
-          done_dwhh = true;
-        }
-        if (want_dx) {  // dX_l (+)= dGi[TB, GH] * W_ih[GH, Il]
-          float* Cx;
-          RowMap cx_rows;
+        const bool tc_wih = dw_ih && aligned_to(dw_ih, 16), tc_whh = dw_hh && aligned_to(dw_hh, 16) && d.T > 1;
+        float* Cx = nullptr;
+        RowMap cx_rows = simple_rows(1);
+        bool tc_dx = false;
+        if (want_dx) {
           if (ln_l0) {
             Cx = S + sl.b_dxln; cx_rows = simple_rows((long long)d.I);
           } else if (l == 0) {
@@ -640,21 +606,59 @@ B200RNN_API int b200rnn_backward_fused(const b200rnn_desc* desc, const float* x,
           } else {
             Cx = S + sl.b_dy; cx_rows = simple_rows((long long)d.DH);
           }
-          const bool ok = (reinterpret_cast<uintptr_t>(Cx) % 16 == 0) && cx_rows.s_outer % 4 == 0 && cx_rows.s_inner % 4 == 0;
-          if (ok) {
-            float* dGs = S + sl.b_tc_dg;  // [TB][GH]
-            float* wT = S + sl.b_tc_wT;   // [Il][GH]
-            rc = tc_split(dG, simple_rows((long long)d.GH), (int)d.TB, (int)d.GH, dGs, dGs + d.TB * d.GH, st);
+          tc_dx = (reinterpret_cast<uintptr_t>(Cx) % 16 == 0) && cx_rows.s_outer % 4 == 0 && cx_rows.s_inner % 4 == 0;
+        }
+        if (tc_wih || tc_whh || tc_dx) {
+          rc = tc_split(dG, simple_rows((long long)d.GH), (int)d.TB, (int)d.GH, dGs, dGs + d.TB * d.GH, st);
+          if (rc) return rc;
+        }
+        if (tc_wih) {  // dW_ih[GH, Il] = sum_tb dG[tb, :]^T X_l[tb, :]
+          const TcOperand opA{dGs, dGs + d.TB * d.GH, (long long)d.GH, true};
+          rc = tc_gemm_presplit(opA, opX, (int)d.GH, Il, (int)d.TB, dw_ih, simple_rows(Il), nullptr, nullptr, 0,
+                                accumulate, S + sl.b_tc_part, sl.b_tc_part_bytes, st);
+          if (rc) return rc;
+          done_dwih = true;
+        }
+        if (tc_whh) {
+          // dW_hh = sum_t dGh[t]^T h_{prev(t)}: rows are (t,b) flattened time-major, so the one-step shift is a ROW
+          // offset of B (forward: dG[t] with y[t-1]; reverse: dG[t] with y[t+1]); rows beyond Kp read as zero (TMA)
+          float* yS = S + sl.b_tc_yT;  // [TB][H]
+          rc = tc_split(bp.y + (long long)k * d.H, tb_rows(bp.y_st, bp.y_sb, d.B), (int)d.TB, d.H, yS,
+                        yS + d.TB * (size_t)d.H, st);
+          if (rc) return rc;
+          const int Kp = (d.T - 1) * d.B;
+          const size_t rowA = (k == 0) ? (size_t)d.B : 0, rowY = (k == 0) ? 0 : (size_t)d.B;
+          const TcOperand opY{yS + rowY * d.H, yS + d.TB * (size_t)d.H + rowY * d.H, (long long)d.H, true};
+          if (d.mode == B200RNN_LSTM) {
+            const TcOperand opA{dGs + rowA * d.GH, dGs + d.TB * d.GH + rowA * d.GH, (long long)d.GH, true};
+            rc = tc_gemm_presplit(opA, opY, (int)d.GH, d.H, Kp, dw_hh, simple_rows(d.H), nullptr, nullptr, 0,
+                                  accumulate, S + sl.b_tc_part, sl.b_tc_part_bytes, st);
             if (rc) return rc;
-            rc = tc_split_transpose(pp[0], simple_rows(Il), (int)d.GH, Il, wT, wT + (size_t)Il * d.GH, (long long)d.GH, st);
+          } else {
+            rc = tc_split(dHN, simple_rows((long long)d.H), (int)d.TB, d.H, hnS, hnS + d.TB * (size_t)d.H, st);
             if (rc) return rc;
-            const TcOperand opA{dGs, dGs + d.TB * d.GH, (long long)d.GH};
-            const TcOperand opB{wT, wT + (size_t)Il * d.GH, (long long)d.GH};
-            rc = tc_gemm_presplit(opA, opB, (int)d.TB, Il, (int)d.GH, Cx, cx_rows, nullptr, nullptr, 0, (k > 0) ? 1 : 0,
-                                  nullptr, 0, st);
+            // columns [0, 2H) of dG: r and z gates
+            const TcOperand opRZ{dGs + rowA * d.GH, dGs + d.TB * d.GH + rowA * d.GH, (long long)d.GH, true};
+            rc = tc_gemm_presplit(opRZ, opY, 2 * d.H, d.H, Kp, dw_hh, simple_rows(d.H), nullptr, nullptr, 0,
+                                  accumulate, S + sl.b_tc_part, sl.b_tc_part_bytes, st);
             if (rc) return rc;
-            done_dx = true;
+            const TcOperand opN{hnS + rowA * d.H, hnS + d.TB * (size_t)d.H + rowA * d.H, (long long)d.H, true};  // n rows: dn * r
+            rc = tc_gemm_presplit(opN, opY, d.H, d.H, Kp, dw_hh + (size_t)2 * d.H * d.H, simple_rows(d.H), nullptr,
+                                  nullptr, 0, accumulate, S + sl.b_tc_part, sl.b_tc_part_bytes, st);
+            if (rc) return rc;
           }
+          done_dwhh = true;
+        }
+        if (tc_dx) {  // dX_l (+)= dG[TB, GH] * W_ih[GH, Il]: A K-major (the same split of dG), B = W_ih as it lies (MN-major)
+          float* wS = S + sl.b_tc_wT;   // [GH][Il] hi, then lo
+          rc = tc_split(pp[0], simple_rows(Il), (int)d.GH, Il, wS, wS + d.GH * (size_t)Il, st);
+          if (rc) return rc;
+          const TcOperand opA{dGs, dGs + d.TB * d.GH, (long long)d.GH, false};
+          const TcOperand opB{wS, wS + d.GH * (size_t)Il, (long long)Il, true};
+          rc = tc_gemm_presplit(opA, opB, (int)d.TB, Il, (int)d.GH, Cx, cx_rows, nullptr, nullptr, 0, (k > 0) ? 1 : 0,
+                                nullptr, 0, st);
+          if (rc) return rc;
+          done_dx = true;
         }
       }
       if (!done_dwih) {  // dW_ih = dGi^T * X_l

@@ -52,12 +52,12 @@ int launch_gemm_tc(const GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t 
 struct TcOperand {
   const float* hi;
   const float* lo;
-  long long ld;  // floats between consecutive rows of the K-major [rows, K] matrices (multiple of 4)
+  long long ld;  // floats between consecutive rows (multiple of 4)
+  bool mn = false;  // false: K-major, dense [M or N rows][K]; true: MN-major, dense [K rows][M or N] (no transpose needed
+                    // for operands whose contraction index is their row index: dG, X, h_prev in the wgrad GEMMs)
 };
 bool tc_available();
 int tc_split(const float* src, const RowMap& rows, int R, int Cc, float* hi, float* lo, cudaStream_t stream);
-int tc_split_transpose(const float* src, const RowMap& rows, int R, int Cc, float* hiT, float* loT, long long ldT,
-                       cudaStream_t stream);
 int tc_gemm_presplit(const TcOperand& A, const TcOperand& B, int M, int N, int K, float* C, const RowMap& c_rows,
                      const float* bias1, const float* bias2, int bias2_n, int accumulate, void* splitk_ws,
                      size_t splitk_ws_bytes, cudaStream_t stream);

@@ -94,6 +94,23 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major tile (the contraction index is the ROW index of the source matrix, e.g. dG [T*B, G*H] as the A operand of
+// dW = dG^T X). For 32-bit operands the only MN-major shared-memory layout tcgen05 accepts is "128-byte swizzle with
+// 32-byte atoms" (descriptor layout type 1; CUTLASS: Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> on byte addresses):
+// rows of 32 floats of M/N (128 B), FOUR K rows per 512-byte atom, inside an atom the 32-byte chunks of a row are
+// XOR-ed with (row & 3) - exactly what a TMA box {32 floats, 32 rows} with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+// deposits. Atoms along K are 512 B apart (SBO), the four 32-wide column blocks of a 128-wide tile 4 KB apart (LBO).
+// One MMA (K = 8) consumes two atoms along K; the next K step starts 1 KB further.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;  // leading byte offset: next 32-wide block along M/N
+  d |= (uint64_t)(512 >> 4) << 32;   // stride byte offset: next 4 K rows
+  d |= (uint64_t)1 << 46;            // descriptor version 1 (sm_100)
+  d |= (uint64_t)1 << 61;            // layout type: SWIZZLE_128B_BASE32B
+  return d;
+}
+
 // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=128, dense, no negate
 constexpr uint32_t IDESC_TF32_128x128 =
     (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -109,6 +126,7 @@ struct TcArgs {
   int nmain;  // hi*hi accumulators in use (1..NMAIN): k-blocks go round-robin over them
   int nsets;  // TMEM accumulator sets (2 when (nmain+1)*BN*2 <= 512: epilogue of tile i overlaps mainloop of i+1)
   int accumulate;   // C += result (splitk == 1 only)
+  int a_mn, b_mn;   // operand is MN-major: source matrix [K rows][M or N contiguous] (wgrad / dgrad without transposes)
   int splitk;       // > 1: work item = (k-split, tile); raw partial sums go to partial[ks][M][N]
   int kb_per_split; // k-blocks per split
   float* partial;
@@ -179,16 +197,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           ptx::mbar_wait(&empty[s], ph ^ 1);
           unsigned char* st = base + s * STAGE_BYTES;
           ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-          tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, kb * BK, m0, &full[s]);
-          tma_load_2d(st + 1 * TILE_BYTES, &map_a_lo, kb * BK, m0, &full[s]);
-          tma_load_2d(st + 2 * TILE_BYTES, &map_b_hi, kb * BK, n0, &full[s]);
-          tma_load_2d(st + 3 * TILE_BYTES, &map_b_lo, kb * BK, n0, &full[s]);
+          if (args.a_mn) {  // four {32 floats of M, BK rows of K} boxes per split half
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              tma_load_2d(st + 0 * TILE_BYTES + j * 4096, &map_a_hi, m0 + 32 * j, kb * BK, &full[s]);
+              tma_load_2d(st + 1 * TILE_BYTES + j * 4096, &map_a_lo, m0 + 32 * j, kb * BK, &full[s]);
+            }
+          } else {
+            tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, kb * BK, m0, &full[s]);
+            tma_load_2d(st + 1 * TILE_BYTES, &map_a_lo, kb * BK, m0, &full[s]);
+          }
+          if (args.b_mn) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              tma_load_2d(st + 2 * TILE_BYTES + j * 4096, &map_b_hi, n0 + 32 * j, kb * BK, &full[s]);
+              tma_load_2d(st + 3 * TILE_BYTES + j * 4096, &map_b_lo, n0 + 32 * j, kb * BK, &full[s]);
+            }
+          } else {
+            tma_load_2d(st + 2 * TILE_BYTES, &map_b_hi, kb * BK, n0, &full[s]);
+            tma_load_2d(st + 3 * TILE_BYTES, &map_b_lo, kb * BK, n0, &full[s]);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (ptx::elect_one_sync()) {
       int it = 0, ti = 0;
+      // instruction descriptor with the operands' major-ness (bit 15: A is MN-major, bit 16: B is MN-major)
+      const uint32_t idesc = IDESC_TF32_128x128 | (args.a_mn ? (1u << 15) : 0u) | (args.b_mn ? (1u << 16) : 0u);
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ti) {
         const int nkb = min(nkb_total, (item / ntiles + 1) * args.kb_per_split) - (item / ntiles) * args.kb_per_split;
         const int set = ti % args.nsets;
@@ -203,17 +239,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           ptx::mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t st = ptx::smem_u32(base + s * STAGE_BYTES);
-          const uint64_t a_hi = make_kmajor_sw128_desc(st + 0 * TILE_BYTES);
-          const uint64_t a_lo = make_kmajor_sw128_desc(st + 1 * TILE_BYTES);
-          const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * TILE_BYTES);
-          const uint64_t b_lo = make_kmajor_sw128_desc(st + 3 * TILE_BYTES);
+          const uint64_t a_hi = args.a_mn ? make_mnmajor_sw128_desc(st + 0 * TILE_BYTES) : make_kmajor_sw128_desc(st + 0 * TILE_BYTES);
+          const uint64_t a_lo = args.a_mn ? make_mnmajor_sw128_desc(st + 1 * TILE_BYTES) : make_kmajor_sw128_desc(st + 1 * TILE_BYTES);
+          const uint64_t b_hi = args.b_mn ? make_mnmajor_sw128_desc(st + 2 * TILE_BYTES) : make_kmajor_sw128_desc(st + 2 * TILE_BYTES);
+          const uint64_t b_lo = args.b_mn ? make_mnmajor_sw128_desc(st + 3 * TILE_BYTES) : make_kmajor_sw128_desc(st + 3 * TILE_BYTES);
           const uint32_t acc_main = acc_set + (uint32_t)((kb % args.nmain) * BN);
+          // K step of 8: K-major = 32 bytes further inside the swizzle atom; MN-major = the next 1 KB atom
+          const uint32_t a_step = args.a_mn ? (1024u >> 4) : (32u >> 4), b_step = args.b_mn ? (1024u >> 4) : (32u >> 4);
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 8 tf32 = 32 bytes along K inside the swizzle atom
-            tc_mma_tf32(acc_cross, a_lo + adv, b_hi + adv, IDESC_TF32_128x128, (kb | k) != 0 ? 1u : 0u);
-            tc_mma_tf32(acc_cross, a_hi + adv, b_lo + adv, IDESC_TF32_128x128, 1u);
-            tc_mma_tf32(acc_main, a_hi + adv, b_hi + adv, IDESC_TF32_128x128, (kb >= args.nmain || k != 0) ? 1u : 0u);
+            const uint64_t adva = (uint64_t)(k * a_step), advb = (uint64_t)(k * b_step);
+            tc_mma_tf32(acc_cross, a_lo + adva, b_hi + advb, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_tf32(acc_cross, a_hi + adva, b_lo + advb, idesc, 1u);
+            tc_mma_tf32(acc_main, a_hi + adva, b_hi + advb, idesc, (kb >= args.nmain || k != 0) ? 1u : 0u);
           }
           tc_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
         }
@@ -462,34 +500,6 @@ __global__ void layernorm_bwd_reduce_kernel(const float* __restrict__ part, int 
   }
 }
 
-// Transposing variant: src [R rows (RowMap), Cc columns]  ->  hiT / loT [Cc][ldT] (element (c, r) at c*ldT + r).
-// Turns the "MN-major" operands of the wgrad GEMMs (dG^T, X^T, H_prev^T) into the K-major form the kernel takes.
-__global__ void split_tf32_transpose_kernel(const float* __restrict__ src, RowMap rows, int R, int Cc,
-                                            float* __restrict__ hiT, float* __restrict__ loT, long long ldT) {
-  __shared__ float tile[32][33];
-  const int tiles_r = (R + 31) / 32, tiles_c = (Cc + 31) / 32;
-  for (int tix = blockIdx.x; tix < tiles_r * tiles_c; tix += gridDim.x) {
-    const int tr = tix / tiles_c, tcn = tix - tr * tiles_c;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-      const int r = tr * 32 + i, c = tcn * 32 + threadIdx.x;
-      tile[i][threadIdx.x] = (r < R && c < Cc) ? __ldg(src + rows.off(r) + c) : 0.f;
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-      const int c = tcn * 32 + i, r = tr * 32 + threadIdx.x;
-      if (c < Cc && r < R) {
-        const float x = tile[threadIdx.x][i];
-        uint32_t t;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
-        const float h = __uint_as_float(t);
-        hiT[(size_t)c * ldT + r] = h;
-        loT[(size_t)c * ldT + r] = x - h;
-      }
-    }
-    __syncthreads();
-  }
-}
-
 // ---- host side -------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -528,6 +538,21 @@ bool make_map(CUtensorMap* map, const float* ptr, int rows, int K, long long ld 
   return r == CUDA_SUCCESS;
 }
 
+// MN-major operand: dense row-major [Krows, MN] fp32 matrix (the contraction index is the row), box = [32 K rows,
+// 32 floats of M/N], 128-byte swizzle; rows beyond Krows and columns beyond MN read as zero
+bool make_map_mn(CUtensorMap* map, const float* ptr, int Krows, int MN, long long ld) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)MN, (cuuint64_t)Krows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 bool tc_disabled() {
   static const bool off = getenv("B200RNN_NO_TC") != nullptr;
   return off;
@@ -539,8 +564,9 @@ size_t gemm_tc_scratch_bytes(int M, int N, int K) { return (size_t)2 * ((size_t)
 
 bool gemm_tc_eligible(const GemmParams& p, size_t ws_bytes) {
   if (tc_disabled()) return false;
-  if (!p.a_kcontig || !p.b_kcontig || p.accumulate) return false;
+  if (p.accumulate) return false;
   if (p.M < 1 || p.K < BK || p.K % BK != 0 || p.N % BN != 0) return false;
+  if (!p.a_kcontig && p.M % 4 != 0) return false;  // MN-major split copies are dense [K][M]: rows must stay 16-byte aligned
   if (ws_bytes < gemm_tc_scratch_bytes(p.M, p.N, p.K)) return false;
   // the epilogue stores float4 along n
   if ((reinterpret_cast<uintptr_t>(p.C) & 15u) || (p.c_rows.s_outer % 4) || (p.c_rows.s_inner % 4)) return false;
@@ -555,18 +581,6 @@ int tc_split(const float* src, const RowMap& rows, int R, int Cc, float* hi, flo
   if (blocks < 1) blocks = 1;
   ProfScope prof(PROF_MISC, stream);
   split_tf32_kernel<<<blocks, 256, 0, stream>>>(src, rows, R, Cc, hi, lo, vec ? 1 : 0);
-  B200_CUDA_CHECK(cudaGetLastError());
-  count_launch();
-  return B200RNN_OK;
-}
-
-int tc_split_transpose(const float* src, const RowMap& rows, int R, int Cc, float* hiT, float* loT, long long ldT,
-                       cudaStream_t stream) {
-  int tiles = ((R + 31) / 32) * ((Cc + 31) / 32);
-  int blocks = tiles < 148 * 8 ? tiles : 148 * 8;
-  if (blocks < 1) blocks = 1;
-  ProfScope prof(PROF_MISC, stream);
-  split_tf32_transpose_kernel<<<blocks, dim3(32, 8), 0, stream>>>(src, rows, R, Cc, hiT, loT, ldT);
   B200_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return B200RNN_OK;
@@ -651,8 +665,11 @@ int tc_gemm_presplit(const TcOperand& A, const TcOperand& B, int M, int N, int K
     return B200RNN_ERR_UNSUPPORTED;
   }
   CUtensorMap m_ahi, m_alo, m_bhi, m_blo;
-  if (!make_map(&m_ahi, A.hi, M, K, A.ld) || !make_map(&m_alo, A.lo, M, K, A.ld) || !make_map(&m_bhi, B.hi, N, K, B.ld) ||
-      !make_map(&m_blo, B.lo, N, K, B.ld)) {
+  const bool ok_a = A.mn ? (make_map_mn(&m_ahi, A.hi, K, M, A.ld) && make_map_mn(&m_alo, A.lo, K, M, A.ld))
+                         : (make_map(&m_ahi, A.hi, M, K, A.ld) && make_map(&m_alo, A.lo, M, K, A.ld));
+  const bool ok_b = B.mn ? (make_map_mn(&m_bhi, B.hi, K, N, B.ld) && make_map_mn(&m_blo, B.lo, K, N, B.ld))
+                         : (make_map(&m_bhi, B.hi, N, K, B.ld) && make_map(&m_blo, B.lo, N, K, B.ld));
+  if (!ok_a || !ok_b) {
     set_error("tc_gemm: cuTensorMapEncodeTiled failed (operands must be 16-byte aligned, ld %% 4 == 0)");
     return B200RNN_ERR_CUDA;
   }
@@ -676,6 +693,8 @@ int tc_gemm_presplit(const TcOperand& A, const TcOperand& B, int M, int N, int K
   a.M = M; a.N = N; a.K = K;
   a.bias1 = bias1; a.bias2 = bias2; a.bias2_n = bias2_n;
   a.accumulate = accumulate;
+  a.a_mn = A.mn ? 1 : 0;
+  a.b_mn = B.mn ? 1 : 0;
   a.tiles_m = (M + BM - 1) / BM;
   a.tiles_n = N / BN;
   const int ntiles = a.tiles_m * a.tiles_n;
@@ -719,17 +738,21 @@ int launch_gemm_tc(const GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t 
   const float* b_hi = p.tc_b_hi;
   const float* b_lo = p.tc_b_lo;
   int rc = B200RNN_OK;
-  if (!p.tc_a_presplit) rc = tc_split(p.A, p.a_rows, p.M, p.K, a_hi, a_lo, stream);
+  // a_kcontig: A is [M rows][K]; else A is [K rows][M] (MN-major): the split copy keeps the source's orientation
+  if (!p.tc_a_presplit)
+    rc = p.a_kcontig ? tc_split(p.A, p.a_rows, p.M, p.K, a_hi, a_lo, stream)
+                     : tc_split(p.A, p.a_rows, p.K, p.M, a_hi, a_lo, stream);
   if (rc) return rc;
   if (!b_hi || !b_lo) {
     float* w_hi = a_lo + (size_t)p.M * p.K;
     float* w_lo = w_hi + (size_t)p.N * p.K;
-    rc = tc_split(p.B, p.b_rows, p.N, p.K, w_hi, w_lo, stream);
+    rc = p.b_kcontig ? tc_split(p.B, p.b_rows, p.N, p.K, w_hi, w_lo, stream)
+                     : tc_split(p.B, p.b_rows, p.K, p.N, w_hi, w_lo, stream);
     if (rc) return rc;
     b_hi = w_hi;
     b_lo = w_lo;
   }
-  TcOperand A{a_hi, a_lo, p.K}, B{b_hi, b_lo, p.K};
+  TcOperand A{a_hi, a_lo, p.a_kcontig ? p.K : p.M, !p.a_kcontig}, B{b_hi, b_lo, p.b_kcontig ? p.K : p.N, !p.b_kcontig};
   return tc_gemm_presplit(A, B, p.M, p.N, p.K, p.C, p.c_rows, p.bias1, p.bias2, p.bias2_n, 0, nullptr, 0, stream);
 }
 

@@ -496,10 +496,11 @@ def run_ours(args) -> None:
     dev_in = [(a.to(dev), t.to(dev), y.to(dev)) for a, t, y in host]
     loss_buf = torch.zeros((), device=dev)
 
-    def train_step(audio, text, labels):
+    def train_step(audio, text, labels, loss_out=None):
+        loss_out = loss_buf if loss_out is None else loss_out
         if fused is not None:
-            out, loss = fused(b200rnn.FuseBatch(audio, text), labels)   # includes the all-reduce and Adam
-            loss_buf.copy_(loss)
+            out, loss = fused(b200rnn.FuseBatch(audio, text), labels)   # includes the gradient exchange and Adam
+            loss_out.copy_(loss)
             return out
         bucket.zero()
         tf, af = model.pretrained_feature(b200rnn.FuseBatch(audio, text))
@@ -508,7 +509,7 @@ def run_ours(args) -> None:
         loss.backward()
         bucket.allreduce()
         opt.step()
-        loss_buf.copy_(loss.detach())
+        loss_out.copy_(loss.detach())
         return out
 
     _log(f"rank {rank}/{world}: model built, host cores usable {usable_cores()} (os.cpu_count {os.cpu_count()})")
@@ -587,6 +588,7 @@ def run_ours(args) -> None:
         lab_host[i].copy_(host[i][2])
         pinned.append((a, t))
     loss_host = torch.zeros(max(K, 1) + W + 4).pin_memory()
+    loss_slot = [torch.zeros((), device=dev) for _ in range(2)]   # per staging slot: read back on the copy stream
     e2e_graphs = []
     if use_graph:
         try:
@@ -594,7 +596,7 @@ def run_ours(args) -> None:
             for s in range(2):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=pool):
-                    train_step(stagers[s].d_audio, stagers[s].d_text, lab_dev[s])
+                    train_step(stagers[s].d_audio, stagers[s].d_text, lab_dev[s], loss_slot[s])
                 e2e_graphs.append(g)
         except Exception:
             e2e_graphs = []
@@ -603,10 +605,40 @@ def run_ours(args) -> None:
     in_ready = [torch.cuda.Event() for _ in range(2)]
     in_free = [torch.cuda.Event() for _ in range(2)]
 
+    # Preferred form of the same pipeline: ONE graph per step that contains the step on staging slot s AND, as a parallel
+    # branch, the pinned-host -> device copy of the NEXT step's inputs into the other slot, and the loss read-back at its
+    # end. No per-step cross-stream events on the launching stream (they cost ~30 us of inter-graph gap per step); the
+    # copies are still made every step, from pinned host memory, inside the timed region.
+    pf_graphs = []
+    loss_pin = [torch.zeros(1).pin_memory() for _ in range(N_ROTATE)]
+    if use_graph and N_ROTATE % 2 == 0:
+        try:
+            pool = graphs[0].pool()
+            for k in range(N_ROTATE):
+                s, ns, nk = k % 2, (k + 1) % 2, (k + 1) % N_ROTATE
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    cur = torch.cuda.current_stream()
+                    copy_stream.wait_stream(cur)
+                    with torch.cuda.stream(copy_stream):
+                        stagers[ns].d_audio.copy_(pinned[nk][0], non_blocking=True)
+                        stagers[ns].d_text.copy_(pinned[nk][1], non_blocking=True)
+                        lab_dev[ns].copy_(lab_host[nk], non_blocking=True)
+                    train_step(stagers[s].d_audio, stagers[s].d_text, lab_dev[s], loss_slot[s])
+                    loss_pin[k].copy_(loss_slot[s].reshape(1), non_blocking=True)
+                    cur.wait_stream(copy_stream)
+                pf_graphs.append(g)
+        except Exception as exc:  # noqa: BLE001
+            _log(f"e2e: prefetch-in-graph capture failed ({type(exc).__name__}: {exc}); using the event pipeline")
+            pf_graphs = []
+            torch.cuda.synchronize()
+
     def e2e_issue_copy(i: int):
         s = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(in_free[s])
+            if i >= 2:   # the loss of the step that last used this slot (step i-2): device -> pinned host, every step
+                loss_host[i - 2:i - 1].copy_(loss_slot[s].reshape(1), non_blocking=True)
             a, t = pinned[i % N_ROTATE]
             stagers[s].d_audio.copy_(a, non_blocking=True)
             stagers[s].d_text.copy_(t, non_blocking=True)
@@ -619,29 +651,47 @@ def run_ours(args) -> None:
         if e2e_graphs:
             e2e_graphs[s].replay()
         else:
-            train_step(stagers[s].d_audio, stagers[s].d_text, lab_dev[s])
+            train_step(stagers[s].d_audio, stagers[s].d_text, lab_dev[s], loss_slot[s])
         in_free[s].record(main)
-        loss_host[i:i + 1].copy_(loss_buf.reshape(1), non_blocking=True)
 
     for s in range(2):
         in_free[s].record(main)
     total = W + K
     _barrier()
-    # warm-up part (untimed), pipeline primed one copy ahead
-    e2e_issue_copy(0)
-    for i in range(W):
-        e2e_issue_copy(i + 1)
-        e2e_compute(i)
-    _barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for i in range(W, total):
-        if i + 1 < total:
+    if pf_graphs:
+        e2e_issue_copy(0)                       # inputs of step 0; every later step's inputs arrive by the graphs
+        main.wait_stream(copy_stream)
+        for i in range(W):
+            pf_graphs[i % N_ROTATE].replay()
+        _barrier()
+        f0.record()
+        for i in range(W, total):
+            pf_graphs[i % N_ROTATE].replay()
+        f1.record()
+        _barrier()
+        loss_host[total - 1] = loss_pin[(total - 1) % N_ROTATE][0]
+    else:
+        # warm-up part (untimed), pipeline primed one copy ahead
+        e2e_issue_copy(0)
+        for i in range(W):
             e2e_issue_copy(i + 1)
-        e2e_compute(i)
-    f1.record()
-    main.wait_stream(copy_stream)
-    _barrier()
+            e2e_compute(i)
+        _barrier()
+        f0.record()
+        for i in range(W, total):
+            if i + 1 < total:
+                e2e_issue_copy(i + 1)
+            e2e_compute(i)
+        # the last two losses are still on the device: read them back inside the timed region as well
+        with torch.cuda.stream(copy_stream):
+            for i in (total - 2, total - 1):
+                if i >= 0:
+                    copy_stream.wait_event(in_free[i % 2])
+                    loss_host[i:i + 1].copy_(loss_slot[i % 2].reshape(1), non_blocking=True)
+        main.wait_stream(copy_stream)
+        f1.record()
+        _barrier()
     # the H2D of the first timed step was issued before f0; charge it by adding one exposed copy time below
     e2e_ms = _max_over_ranks(f0.elapsed_time(f1), dev)
     h2d_bytes = stagers[0].h2d_bytes + B_PER_GPU * 8
@@ -671,8 +721,12 @@ def run_ours(args) -> None:
         "gpu_launches_per_step": int(launches_per_step),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms_total / K, "h2d_ms_alone": one_copy_ms,
-                "how": "pinned host -> device copies double-buffered on a copy stream, graph replay of the step, "
-                       "loss copied back to pinned memory every step; first copy of the timed region added unoverlapped",
+                "how": ("one CUDA graph per step = the step on staging slot s + (parallel branch) the pinned-host -> device "
+                        "copy of the next step's inputs into the other slot + the loss read-back to pinned memory; "
+                        if pf_graphs else
+                        "pinned host -> device copies double-buffered on a copy stream with events, graph replay of the "
+                        "step, every step's loss copied back to pinned memory on the copy stream; ") +
+                       "first copy of the timed region added unoverlapped",
                 "final_loss": final_loss},
     }
 
@@ -752,6 +806,7 @@ def run_ours(args) -> None:
                           f"(oracle/ref_models.py on stock torch.nn CPU kernels, {cores} threads); with the reference's "
                           f"list->tensor conversion (fuse_net_whole.py:343) it is {v2:.1f} seq/s ({ms2:.0f} ms/step)"}
         _emit(line)
+    pf_graphs.clear()
     _teardown(graphs, e2e_graphs, world, fused)
 
 

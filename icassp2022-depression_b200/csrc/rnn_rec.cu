@@ -32,6 +32,16 @@ namespace b200rnn {
 namespace {
 
 constexpr int MAX_SMEM = 232448;  // 227 KB opt-in limit per CTA on sm_100
+// The CTA's own state slice is delivered locally (st.shared + mbarrier.arrive per warp). -DB200RNN_SELF_VIA_CLUSTER
+// builds the round-1 behaviour (own slice through st.async like the peers'): compute-sanitizer's racecheck does not
+// model the ordering that inline-PTX mbarrier.arrive / try_wait give to ordinary shared-memory stores and flags every
+// local store / LDS pair of the default build, so the race-free evidence of the REST of the kernel is taken on that
+// build (profiles/README.md); the ordering argument for the local path is in allgather_units' comment.
+#ifdef B200RNN_SELF_VIA_CLUSTER
+constexpr bool kLocalSelf = false;
+#else
+constexpr bool kLocalSelf = true;
+#endif
 constexpr unsigned FULLMASK = 0xffffffffu;
 
 template <int MODE, int H, int C, int BS, int KL, int UPL, int RG>
@@ -67,6 +77,10 @@ struct RecCfg {
 // CTA's own copy does not take the trip through the cluster network (measured: >= 600 cycles from the store to the
 // barrier flip even for the own CTA, tools/trace_rec.py): it is written with ordinary st.shared and published with one
 // mbarrier.arrive per warp on the own-source barrier (initialised with the warp count instead of a byte count).
+// Ordering of the local path: RAW - readers pass mbarrier.try_wait (acquire) on that barrier, which completes only
+// after every warp's arrive (release) that follows its st.shared + __syncwarp. WAR - a warp writes buffer b at the end
+// of step s; the last readers of b ran in step s-1's contraction, and no warp can leave chunk 0 of step s before all
+// NW warps have arrived for step s-1, i.e. finished that contraction.
 template <int C, int KL, int UPL, int BS, bool LOCAL_SELF = false>
 __device__ __forceinline__ void allgather_units(float val, float* vec_local, int vstride, int col0,
                                                 uint64_t* bar_local, int lane, uint32_t rank = 0) {
@@ -133,7 +147,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     // [0]: weights (tx bytes). [1 + buf*C + src]: slice of source CTA `src` - remote sources complete tx bytes
     // (one arrive.expect_tx by thread 0 per phase), the CTA's OWN slice is published by one plain arrive per warp
     for (int i = 0; i < Cfg::NBAR; ++i)
-      ptx::mbar_init(&bars[i], (i >= 1 && (uint32_t)((i - 1) % C) == rank) ? (uint32_t)Cfg::NW : 1u);
+      ptx::mbar_init(&bars[i], (kLocalSelf && i >= 1 && (uint32_t)((i - 1) % C) == rank) ? (uint32_t)Cfg::NW : 1u);
     ptx::fence_mbar_init();
   }
   __syncthreads();
@@ -247,7 +261,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     if (tid == 0 && step + 1 < T) {
 #pragma unroll
       for (int src = 0; src < C; ++src)
-        if ((uint32_t)src != rank)
+        if (!kLocalSelf || (uint32_t)src != rank)
           ptx::mbar_arrive_expect_tx(&bars[1 + nxt * C + src], (uint32_t)(BS * HS * sizeof(float)));
     }
     if constexpr (PACK2) fold_pairs<G, UPL, BS>(acc2, acc);
@@ -290,7 +304,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     if (tr) trow[6] = clock64() + (long long)(hnew == 12345.678f);          // gate math done
 
     if (step + 1 < T)
-      allgather_units<C, KL, UPL, BS, true>(hnew, h_nxt, H, j0 + w * UPW, &bars[1 + nxt * C + rank], lane, rank);
+      allgather_units<C, KL, UPL, BS, kLocalSelf>(hnew, h_nxt, H, j0 + w * UPW, &bars[1 + nxt * C + rank], lane, rank);
     if (tr) trow[7] = clock64();                                            // exchange issued
 
     // prefetch of the next step's x-projection (long latency, consumed at the next gate math); this step's global
@@ -365,7 +379,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
   if (tid == 0) {
     // as in the forward: the own slice is delivered locally (G gate-gradient slices x NW warps arrive per phase)
     for (int i = 0; i < Cfg::NBAR; ++i)
-      ptx::mbar_init(&bars[i], (i >= 1 && (uint32_t)((i - 1) % C) == rank) ? (uint32_t)(Cfg::NW * G) : 1u);
+      ptx::mbar_init(&bars[i], (kLocalSelf && i >= 1 && (uint32_t)((i - 1) % C) == rank) ? (uint32_t)(Cfg::NW * G) : 1u);
     ptx::fence_mbar_init();
   }
   __syncthreads();
@@ -435,7 +449,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     if (tid == 0 && !last) {
 #pragma unroll
       for (int src = 0; src < C; ++src)
-        if ((uint32_t)src != rank)
+        if (!kLocalSelf || (uint32_t)src != rank)
           ptx::mbar_arrive_expect_tx(&bars[1 + buf * C + src], (uint32_t)(BS * G * HS * sizeof(float)));
     }
 
@@ -492,8 +506,8 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
         float v = dg[g];
         if (MODE == B200RNN_GRU && g == 2) v = dhn;
         if (!valid) v = 0.f;
-        allgather_units<C, KL, UPL, BS, true>(v, d_buf, GH, g * H + j0 + w * UPW, &bars[1 + buf * C + rank], lane,
-                                              rank);
+        allgather_units<C, KL, UPL, BS, kLocalSelf>(v, d_buf, GH, g * H + j0 + w * UPW, &bars[1 + buf * C + rank],
+                                                    lane, rank);
       }
     }
 

@@ -68,3 +68,28 @@ def test_layernorm_prologue_widths(I):
     assert (ln_m.bias.grad.cpu() - ln_r.bias.grad).abs().max().item() <= 1e-4 * ln_r.bias.grad.abs().max().item()
     with torch.no_grad():   # the no-grad fused path (pooled only, nothing saved)
         assert (gru_m.forward_ln_sum(xm.detach(), ln_m).cpu() - pr.detach()).abs().max().item() < 1e-4
+
+
+def test_recurrence_is_bitwise_deterministic_over_repeated_runs():
+    """The own-slice delivery of the persistent kernels is ordered by mbarrier arrive / try_wait only (no block
+    barrier): a missing ordering would show as run-to-run differences. 40 repetitions of forward + backward, GRU and
+    BiLSTM, must be bit-identical (the split-K and bias reductions are fixed-order as well)."""
+    import b200rnn
+
+    torch.manual_seed(9)
+    for kind, B, T, I, H, bi in (("gru", 128, 60, 256, 256, False), ("lstm", 64, 30, 256, 128, True)):
+        cls = b200rnn.GRU if kind == "gru" else b200rnn.LSTM
+        m = cls(I, H, num_layers=2, bidirectional=bi, batch_first=True).to(DEV)
+        x = torch.randn(B, T, I, device=DEV, requires_grad=True)
+        ref = None
+        for _ in range(40):
+            m.zero_grad()
+            x.grad = None
+            y = m(x)[0]
+            y.square().sum().backward()
+            got = [y.detach().clone(), x.grad.clone()] + [p.grad.clone() for p in m.parameters()]
+            if ref is None:
+                ref = got
+            else:
+                for a, b in zip(got, ref):
+                    assert torch.equal(a, b), kind

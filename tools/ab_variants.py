@@ -1,11 +1,12 @@
 #!/usr/bin/env python
-"""A/B of recurrence variants on ONE box (box-to-box variance is ~3-10 %, so never compare across gpurun calls).
+"""A/B of library switches on ONE box (box-to-box variance is ~2-5 %, so never compare across gpurun calls).
 
-For every variant: parity of the GRU cases against torch CPU (tools/tc_rec_check.py gru) and a short bench.py run
+For every setting: parity of the GRU cases against torch CPU (tools/tc_rec_check.py gru) and a short bench.py run
 (--quick --no-cpu-baseline), each in its own process because the switches are read once per process.
 
-    python tools/ab_variants.py                       # default vs the tensor-memory-assisted FFMA kernel (variant 6)
-    python tools/ab_variants.py FWD_VARIANT=0 FWD_VARIANT=6 REC_TC=1
+    python tools/ab_variants.py                       # FFMA recurrence vs the tcgen05 recurrence forced on
+    python tools/ab_variants.py REC_TC=0 REC_TC=1 NO_TC=1
+(round 1 used it for the B200RNN_FWD_VARIANT tuning variants, all measured slower and removed in round 2)
 """
 import json
 import os
@@ -13,7 +14,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-specs = sys.argv[1:] or ["FWD_VARIANT=0", "FWD_VARIANT=6"]
+specs = sys.argv[1:] or ["REC_TC=0", "REC_TC=1"]
 rows = []
 for spec in specs:
     k, v = spec.split("=")

@@ -25,3 +25,23 @@ for kind, I, H, L, bi in (("gru", 64, 256, 2, False), ("lstm", 64, 128, 2, True)
         m.eval()(x)
     torch.cuda.synchronize()
     print(kind, H, "ok", flush=True)
+# round 2: the fused shells (LayerNorm prologue + pooled gradient under autograd, attention pooling fwd/bwd, Softmax+CE,
+# MN-major wgrad GEMMs, the single-launch fuse head with Adam)
+cfg = dict(num_classes=2, dropout=0.3, rnn_layers=2, embedding_size=256, hidden_dims=128)
+am = b200rnn.AudioBiLSTM(cfg).to(dev).train()
+xa = torch.randn(5, 7, 256, device=dev, requires_grad=True)
+p, loss = b200rnn.softmax_cross_entropy(am.forward_logits(xa), torch.randint(0, 2, (5,), device=dev))
+loss.backward()
+tm = b200rnn.TextBiLSTM(dict(num_classes=2, dropout=0.3, rnn_layers=2, embedding_size=128, hidden_dims=128)).to(dev).train()
+xt = torch.randn(5, 6, 128, device=dev, requires_grad=True)
+tm(xt).sum().backward()
+fm = b200rnn.fusion_net(128, 128, 2, 0.3, 2, 128, 128).to(dev).train()
+for q in fm.parameters():
+    q.requires_grad = False
+fm.fc_final[0].weight.requires_grad = True
+st = b200rnn.FusedFuseStep(fm, lr=1e-3)
+for _ in range(2):
+    st(b200rnn.FuseBatch(torch.randn(6, 5, 128, device=dev), torch.randn(6, 4, 128, device=dev)),
+       torch.randint(0, 2, (6,), device=dev))
+torch.cuda.synchronize()
+print("sanitize_paths done")

@@ -81,7 +81,21 @@ __global__ void bias_reduce_kernel(const float* __restrict__ part, int nslices, 
   if (c >= GH) return;
   float s = 0.f, sn = 0.f;
   const bool gru_n = (mode == B200RNN_GRU) && c >= 2 * H;
-  for (int k = 0; k < nslices; ++k) {  // fixed order => deterministic
+  int k = 0;
+  for (; k + 8 <= nslices; k += 8) {  // 8 independent loads in flight, added in a fixed order => deterministic
+    float v[8], vn[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      v[u] = part[(size_t)(k + u) * W + c];
+      vn[u] = gru_n ? part[(size_t)(k + u) * W + GH + (c - 2 * H)] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      s += v[u];
+      sn += vn[u];
+    }
+  }
+  for (; k < nslices; ++k) {
     s += part[(size_t)k * W + c];
     if (gru_n) sn += part[(size_t)k * W + GH + (c - 2 * H)];
   }

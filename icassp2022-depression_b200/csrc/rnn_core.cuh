@@ -173,6 +173,99 @@ __device__ __forceinline__ void fold_pairs(const float2 (&acc2)[NR][UPL][BS], fl
       for (int ab = 0; ab < BS; ++ab) acc[r][au][ab] = acc2[r][au][ab].x + acc2[r][au][ab].y;
 }
 
+// ---- batch-paired packed contraction (forward GRU) --------------------------------------------------------------
+// dots_chunk2 pairs two k of ONE (row, batch) in an FFMA2, which costs a float2 accumulator per (row, batch) (96
+// registers for the GRU) and a pair fold before the butterfly. Pairing two BATCH rows instead makes both halves of the
+// float2 final outputs: half the accumulator registers, no fold, and the weight becomes a 32-bit operand broadcast to
+// both halves (ptxas emits `FFMA2 Rd, Rw.F32, Rh.F32x2, Rd.F32x2`). For that the two batch values of one k must be an
+// aligned 64-bit word in shared memory, so the state vector is kept in a paired layout:
+//   index(j, b) = ((((j / CW) * 4 + j % 4) * (BS/2) + b / 2) * KL + (j % CW) / 4) * 2 + b % 2,   CW = 4*KL
+// i.e. for a fixed (chunk, e = k % 4, batch pair) the KL k-lanes read KL consecutive 8-byte words (conflict free).
+// Slot am of a lane holds batch pair am ^ (q >> 1); the low bit of q is resolved by the last butterfly stage.
+template <int KL, int BS>
+__device__ __forceinline__ int paired_index(int j, int b) {
+  constexpr int CW = 4 * KL;
+  return ((((j / CW) * 4 + (j & 3)) * (BS / 2) + (b >> 1)) * KL + (j % CW) / 4) * 2 + (b & 1);
+}
+
+template <int NR, int RG, int KL, int UPL, int BS, int KLEN>
+__device__ __forceinline__ void dots_chunk2b(const float* __restrict__ W_s, int group_stride, int row0,
+                                             const float (&wreg)[RG > 0 ? RG : 1][UPL][KLEN / KL],
+                                             const float* __restrict__ vec_s, int c, int ca, int lane,
+                                             float2 (&acc)[NR][UPL][BS / 2]) {
+  using LM = LaneMap<KL, UPL, BS>;
+  constexpr int NP = BS / 2;
+  const int kl = LM::kl(lane), p = LM::p(lane), qh = LM::q(lane) >> 1, cgrp = LM::cl(lane);
+  const int koff = ca * 4 * KL + kl * 4;
+  float2 hp[4][NP];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int am = 0; am < NP; ++am)
+      hp[e][am] = *reinterpret_cast<const float2*>(&vec_s[(((ca * 4 + e) * NP + (am ^ qh)) * KL + kl) * 2]);
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+#pragma unroll
+    for (int au = 0; au < UPL; ++au) {
+      float4 wv;
+      if (r < NR - RG) {
+        const int row = r * group_stride + row0 + cgrp * UPL + (au ^ p);
+        wv = *reinterpret_cast<const float4*>(&W_s[row * KLEN + koff]);
+      } else {
+        const int ri = (r - (NR - RG)) > 0 ? (r - (NR - RG)) : 0;
+        wv = make_float4(wreg[ri][au][c * 4 + 0], wreg[ri][au][c * 4 + 1], wreg[ri][au][c * 4 + 2],
+                         wreg[ri][au][c * 4 + 3]);
+      }
+#pragma unroll
+      for (int am = 0; am < NP; ++am) {
+        float2 a = acc[r][au][am];
+        a = __ffma2_rn(make_float2(wv.x, wv.x), hp[0][am], a);
+        a = __ffma2_rn(make_float2(wv.y, wv.y), hp[1][am], a);
+        a = __ffma2_rn(make_float2(wv.z, wv.z), hp[2][am], a);
+        a = __ffma2_rn(make_float2(wv.w, wv.w), hp[3][am], a);
+        acc[r][au][am] = a;
+      }
+    }
+  }
+}
+
+// Butterfly of the batch-paired accumulators: the same stages as warp_transpose_reduce over units and batch PAIRS, then
+// one last exchange with lane ^ 1 in which the even lane keeps the pair's first batch and the odd lane its second.
+// out[r] = full sum for unit LaneMap::unit(lane), batch LaneMap::q(lane).
+template <int NR, int KL, int UPL, int BS>
+__device__ __forceinline__ void warp_transpose_reduce2b(float2 (&acc)[NR][UPL][BS / 2], float (&out)[NR], int lane) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int NP = BS / 2;
+  const bool odd = (lane & 1) != 0;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    int off = KL / 2;
+#pragma unroll
+    for (int s = UPL / 2; s >= 1; s >>= 1) {
+#pragma unroll
+      for (int au = 0; au < s; ++au)
+#pragma unroll
+        for (int am = 0; am < NP; ++am) {
+          acc[r][au][am].x += __shfl_xor_sync(FULL, acc[r][au + s][am].x, off);
+          acc[r][au][am].y += __shfl_xor_sync(FULL, acc[r][au + s][am].y, off);
+        }
+      off >>= 1;
+    }
+#pragma unroll
+    for (int s = NP / 2; s >= 1; s >>= 1) {
+#pragma unroll
+      for (int am = 0; am < s; ++am) {
+        acc[r][0][am].x += __shfl_xor_sync(FULL, acc[r][0][am + s].x, off);
+        acc[r][0][am].y += __shfl_xor_sync(FULL, acc[r][0][am + s].y, off);
+      }
+      off >>= 1;
+    }
+    const float mine = odd ? acc[r][0][0].y : acc[r][0][0].x;
+    const float send = odd ? acc[r][0][0].x : acc[r][0][0].y;
+    out[r] = mine + __shfl_xor_sync(FULL, send, 1);
+  }
+}
+
 // Transposing butterfly over the KL k-lanes. On return acc[r][0][0] of a lane holds the full sum for
 // unit LaneMap::unit(lane), batch LaneMap::q(lane).
 template <int NR, int KL, int UPL, int BS>

@@ -81,13 +81,16 @@ struct RecCfg {
 // after every warp's arrive (release) that follows its st.shared + __syncwarp. WAR - a warp writes buffer b at the end
 // of step s; the last readers of b ran in step s-1's contraction, and no warp can leave chunk 0 of step s before all
 // NW warps have arrived for step s-1, i.e. finished that contraction.
-template <int C, int KL, int UPL, int BS, bool LOCAL_SELF = false>
+// PAIRED: the destination uses the batch-paired layout of rnn_core.cuh (paired_index): one 16-byte store carries units
+// j and j+4 for the two batch rows of a pair (j % 8 < 4; both land in adjacent k-lanes of the same chunk row).
+template <int C, int KL, int UPL, int BS, bool LOCAL_SELF = false, bool PAIRED = false>
 __device__ __forceinline__ void allgather_units(float val, float* vec_local, int vstride, int col0,
                                                 uint64_t* bar_local, int lane, uint32_t rank = 0) {
   using LM = LaneMap<KL, UPL, BS>;
   constexpr int UPW = LM::UPW;
   constexpr int NCH = UPW * BS / 4;  // 16-byte chunks per destination
   constexpr int NST = C * NCH;
+  static_assert(!PAIRED || (UPW % 8 == 0 && BS % 2 == 0), "paired layout: 8 units per store group, even batch slice");
   const uint32_t bar_addr = ptx::smem_u32(bar_local);
 #pragma unroll
   for (int it = 0; it < (NST + 31) / 32; ++it) {
@@ -95,14 +98,25 @@ __device__ __forceinline__ void allgather_units(float val, float* vec_local, int
     const bool act = idx < NST;
     const int id2 = act ? idx : 0;
     const int r = id2 / NCH, ch = id2 % NCH;
-    const int b = ch / (UPW / 4), quad = ch % (UPW / 4);
     float4 v;
-    v.x = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 0, b));
-    v.y = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 1, b));
-    v.z = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 2, b));
-    v.w = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 3, b));
+    float* dst_ptr;
+    if constexpr (PAIRED) {
+      const int pr = ch % (BS / 2), ue = ch / (BS / 2);   // batch pair, unit slot (group of 8 units, e = unit % 4)
+      const int u = (ue / 4) * 8 + (ue % 4);
+      v.x = __shfl_sync(FULLMASK, val, LM::lane_of(u, 2 * pr));
+      v.y = __shfl_sync(FULLMASK, val, LM::lane_of(u, 2 * pr + 1));
+      v.z = __shfl_sync(FULLMASK, val, LM::lane_of(u + 4, 2 * pr));
+      v.w = __shfl_sync(FULLMASK, val, LM::lane_of(u + 4, 2 * pr + 1));
+      dst_ptr = &vec_local[paired_index<KL, BS>(col0 + u, 2 * pr)];
+    } else {
+      const int b = ch / (UPW / 4), quad = ch % (UPW / 4);
+      v.x = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 0, b));
+      v.y = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 1, b));
+      v.z = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 2, b));
+      v.w = __shfl_sync(FULLMASK, val, LM::lane_of(quad * 4 + 3, b));
+      dst_ptr = &vec_local[b * vstride + col0 + quad * 4];
+    }
     if (act) {
-      float* dst_ptr = &vec_local[b * vstride + col0 + quad * 4];
       if (LOCAL_SELF && (uint32_t)r == rank) {
         *reinterpret_cast<float4*>(dst_ptr) = v;
       } else {
@@ -121,7 +135,9 @@ __device__ __forceinline__ void allgather_units(float val, float* vec_local, int
 // forward
 // =================================================================================================
 // VL = true: per-sequence lengths (PackedSequence semantics): past its length a sequence keeps its state and emits 0
-template <int MODE, int H, int C, int BS, int KL, int UPL, int RG, bool VL = false>
+// PB = true: batch-paired FFMA2 contraction and state layout (rnn_core.cuh, dots_chunk2b); used where it measured
+// faster (GRU H=256 4-row clusters, LSTM H=256), see launch_rec_fwd
+template <int MODE, int H, int C, int BS, int KL, int UPL, int RG, bool VL = false, bool PB = false>
 __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     rec_fwd_kernel(const RecFwdParams p, const int nslices) {
   using Cfg = RecCfg<MODE, H, C, BS, KL, UPL, RG>;
@@ -222,11 +238,15 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     long long* trow = p.trace + ((size_t)step * 8 + (w & 7)) * 8;
     if (tr) trow[0] = clock64();
 
-    // FFMA2 (two fp32 FMAs per issue slot) for the GRU only. Measured on the LSTM H=128 forward (same box, round 2):
+    // FFMA2 (two fp32 FMAs per issue slot) for the GRU only: k-paired (PACK2: float2 = even-k / odd-k partial sums of
+    // one output, folded before the butterfly) or batch-paired (PACKB: float2 = two batch rows of one unit, weight as
+    // a broadcast 32-bit operand, state kept in the paired shared-memory layout). Measured on the LSTM H=128 forward (same box, round 2):
     // FFMA2 53.6 us vs scalar FFMA 49.5 us per layer - with three distinct 64-bit register operands an FFMA2 issues
     // every 3 cycles (register-file bandwidth), and the 4-gate packed accumulators leave the scheduler less room
-    constexpr bool PACK2 = (MODE == B200RNN_GRU) && RG < 2;
+    constexpr bool PACKB = PB;
+    constexpr bool PACK2 = !PACKB && (MODE == B200RNN_GRU) && RG < 2;
     float2 acc2[PACK2 ? G : 1][UPL][BS];
+    float2 acc2b[PACKB ? G : 1][UPL][BS / 2];
     float acc[G][UPL][BS];
 #pragma unroll
     for (int g = 0; g < G; ++g)
@@ -236,6 +256,7 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
         for (int ab = 0; ab < BS; ++ab) {
           acc[g][au][ab] = 0.f;
           if (PACK2) acc2[g][au][ab] = make_float2(0.f, 0.f);
+          if (PACKB && ab < BS / 2) acc2b[g][au][ab] = make_float2(0.f, 0.f);
         }
     // contraction over h, one chunk at a time, starting with the slice this CTA produced itself; a chunk is
     // touched only after the slice(s) it belongs to have arrived (per-source mbarriers)
@@ -251,7 +272,9 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
         }
       }
       if (tr && c < 4) trow[1 + c] = clock64();     // slice of chunk c has arrived (this warp passed its wait)
-      if constexpr (PACK2)
+      if constexpr (PACKB)
+        dots_chunk2b<G, RG, KL, UPL, BS, H>(W_s, HS, w * UPW, wreg, h_cur, c, ca, lane, acc2b);
+      else if constexpr (PACK2)
         dots_chunk2<G, RG, KL, UPL, BS, H, H>(W_s, HS, w * UPW, wreg, h_cur, c, ca, lane, acc2);
       else
         dots_chunk<G, RG, KL, UPL, BS, H, H>(W_s, HS, w * UPW, wreg, h_cur, c, ca, lane, acc);
@@ -264,8 +287,15 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
         if (!kLocalSelf || (uint32_t)src != rank)
           ptx::mbar_arrive_expect_tx(&bars[1 + nxt * C + src], (uint32_t)(BS * HS * sizeof(float)));
     }
-    if constexpr (PACK2) fold_pairs<G, UPL, BS>(acc2, acc);
-    warp_transpose_reduce<G, KL, UPL, BS>(acc);
+    if constexpr (PACKB) {
+      float red[G];
+      warp_transpose_reduce2b<G, KL, UPL, BS>(acc2b, red, lane);
+#pragma unroll
+      for (int g = 0; g < G; ++g) acc[g][0][0] = red[g];
+    } else {
+      if constexpr (PACK2) fold_pairs<G, UPL, BS>(acc2, acc);
+      warp_transpose_reduce<G, KL, UPL, BS>(acc);
+    }
     if (tr) trow[5] = clock64() + (long long)(acc[0][0][0] == 12345.678f);  // butterfly done (value dependence pins it)
 
     float hnew, s0, s1, s2, s3 = 0.f, sx;
@@ -304,7 +334,8 @@ __global__ void __launch_bounds__(RecCfg<MODE, H, C, BS, KL, UPL, RG>::NT, 1)
     if (tr) trow[6] = clock64() + (long long)(hnew == 12345.678f);          // gate math done
 
     if (step + 1 < T)
-      allgather_units<C, KL, UPL, BS, kLocalSelf>(hnew, h_nxt, H, j0 + w * UPW, &bars[1 + nxt * C + rank], lane, rank);
+      allgather_units<C, KL, UPL, BS, kLocalSelf, PACKB>(hnew, h_nxt, H, j0 + w * UPW, &bars[1 + nxt * C + rank], lane,
+                                                         rank);
     if (tr) trow[7] = clock64();                                            // exchange issued
 
     // prefetch of the next step's x-projection (long latency, consumed at the next gate math); this step's global
@@ -653,11 +684,12 @@ int max_active_clusters(K kernel, int C, int NT, size_t smem) {
   return n;
 }
 
-template <int MODE, int H, int C, int BS, int KL, int UPL, int RG>
+template <int MODE, int H, int C, int BS, int KL, int UPL, int RG, bool PB = false>
 bool try_fwd(const RecFwdParams& p, cudaStream_t s, bool force, int* rc) {
   using Cfg = RecCfg<MODE, H, C, BS, KL, UPL, RG>;
   static_assert(Cfg::FWD_SMEM <= MAX_SMEM, "forward config does not fit an SM");
-  auto k = p.lengths ? rec_fwd_kernel<MODE, H, C, BS, KL, UPL, RG, true> : rec_fwd_kernel<MODE, H, C, BS, KL, UPL, RG, false>;
+  auto k = p.lengths ? rec_fwd_kernel<MODE, H, C, BS, KL, UPL, RG, true, PB>
+                     : rec_fwd_kernel<MODE, H, C, BS, KL, UPL, RG, false, PB>;
   const int nslices = (p.B + BS - 1) / BS;
   const int nclusters = nslices * p.D;
   static const bool debug = getenv("B200RNN_DEBUG") != nullptr;
@@ -698,7 +730,7 @@ int env_variant(const char* name, int dflt) {
 }
 
 // Batch-size-aware dispatch (measured on one box, GRU H=256, T=120, per layer launch; profiles/README.md):
-//   B = 128 : FFMA <C=4,BS=4> 222 us | tcgen05 recurrence 354 us
+//   B = 128 : FFMA <C=4,BS=4> 222 us (215 us with the batch-paired FFMA2 form) | tcgen05 recurrence 354 us
 //   B =  64 : FFMA <C=4,BS=4> 215 us (64 CTAs: 43 % of the chip) | FFMA <C=4,BS=2> 175 us (128 CTAs, half the FFMA per step)
 //   B <= 48 : FFMA <C=4,BS=4> 209 us | tcgen05 ~205-215 us | FFMA <C=4,BS=2> 170 us
 // so: clusters of 2 batch rows whenever they fit one wave (B <= ~72), clusters of 4 above, and the tensor-core
@@ -726,7 +758,10 @@ int launch_rec_fwd(const RecFwdParams& p, cudaStream_t s) {
     // FFMA work per step (all three gate blocks in shared memory, 4 warps per CTA)
     static const int bs2 = env_variant("B200RNN_GRU_BS2", 1);  // =0: A/B switch
     if (bs2 && p.B <= 74 && try_fwd<B200RNN_GRU, 256, 4, 2, 16, 8, 0>(p, s, false, &rc)) return rc;
-    if (try_fwd<B200RNN_GRU, 256, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;  // 222 us at B=128, T=120
+    // batch-paired FFMA2 (rnn_core.cuh dots_chunk2b): 215 us at B=128, T=120 against 222 us for the k-paired form on
+    // the same box. The same change measured SLOWER for the 2-row clusters (0.408 vs 0.397 ms per 2-layer forward at
+    // B=64) and with two gate blocks in registers (0.549 vs 0.539 ms), so only this config uses it.
+    if (try_fwd<B200RNN_GRU, 256, 4, 4, 16, 4, 1, true>(p, s, false, &rc)) return rc;
     try_fwd<B200RNN_GRU, 256, 8, 8, 32, 4, 1>(p, s, true, &rc);
     return rc;
   }
@@ -736,11 +771,13 @@ int launch_rec_fwd(const RecFwdParams& p, cudaStream_t s) {
     return rc;
   }
   if (p.mode == B200RNN_LSTM && p.H == 256) {
-    if (try_fwd<B200RNN_LSTM, 256, 4, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
+    // batch-paired FFMA2: 0.238 vs 0.242 ms per 2-layer BiLSTM forward (B=64, T=30) for the scalar-FFMA form
+    if (try_fwd<B200RNN_LSTM, 256, 4, 4, 16, 4, 1, true>(p, s, false, &rc)) return rc;
     try_fwd<B200RNN_LSTM, 256, 8, 8, 16, 2, 1>(p, s, true, &rc);
     return rc;
   }
   if (p.mode == B200RNN_LSTM && p.H == 128) {
+    // scalar FFMA: the batch-paired FFMA2 form measured 0.185 vs 0.180 ms per 2-layer BiLSTM forward (B=128, T=30)
     if (try_fwd<B200RNN_LSTM, 128, 2, 4, 16, 4, 1>(p, s, false, &rc)) return rc;
     try_fwd<B200RNN_LSTM, 128, 4, 8, 16, 2, 1>(p, s, true, &rc);
     return rc;

@@ -2,6 +2,7 @@
 """Small shapes through every recurrence variant, for compute-sanitizer (memcheck / racecheck):
     compute-sanitizer --tool memcheck python tools/sanitize_paths.py
     B200RNN_REC_TC=1 compute-sanitizer --tool racecheck python tools/sanitize_paths.py
+    B200RNN_GRU_BS2=0 compute-sanitizer --tool memcheck python tools/sanitize_paths.py rnn   # recurrence only, 4-row GRU clusters
 """
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -25,6 +26,8 @@ for kind, I, H, L, bi in (("gru", 64, 256, 2, False), ("lstm", 64, 128, 2, True)
         m.eval()(x)
     torch.cuda.synchronize()
     print(kind, H, "ok", flush=True)
+if sys.argv[1:] == ["rnn"]:
+    sys.exit(0)
 # round 2: the fused shells (LayerNorm prologue + pooled gradient under autograd, attention pooling fwd/bwd, Softmax+CE,
 # MN-major wgrad GEMMs, the single-launch fuse head with Adam)
 cfg = dict(num_classes=2, dropout=0.3, rnn_layers=2, embedding_size=256, hidden_dims=128)
